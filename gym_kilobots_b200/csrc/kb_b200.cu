@@ -1,0 +1,942 @@
+// kb_b200.cu -- C-ABI (include/kb_b200.h) + kernels of the B200-native batched Kilobots step.
+//
+// Host side: turns the scene description into the device template (hull / normals / centroid /
+// mass data exactly as Box2D 2.3.x derives them at fixture creation -- b2PolygonShape::Set,
+// ComputeMass, b2Body::ResetMassData; reached from gym_kilobots/lib/body.py:136-142,187-192,
+// 245-251), sizes the per-env state image, and launches one lane group per environment.
+// There is no CPU fallback: without an sm_100 device kb_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kb_toi.cuh"
+
+namespace kb {
+
+// ----------------------------------------------------------------------------------- kernels
+template <int LPE>
+__global__ void __launch_bounds__(128) kb_step_kernel(const __grid_constant__ KernelArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int EPB = 128 / LPE;
+  const int slot = threadIdx.x / LPE;
+  const int env = blockIdx.x * EPB + slot;
+  if (env >= a.numEnvs) return;
+  Sim<LPE> s(a.L);
+  s.g.init();
+  s.sm = smem + (size_t)slot * a.L.smemWords;
+  s.blob = a.blobs + (size_t)env * a.L.blobWords;
+  const int scene = a.envScene ? a.envScene[env] : 0;
+  s.px = a.proxies + (size_t)scene * a.L.Pp;
+  s.bc = a.bodies + (size_t)scene * a.L.Bp;
+  s.lights = a.lights;
+  s.S = a.L.B;
+  s.loadState();
+  s.initScratch();
+  const int A = a.actionMode == KB_ACTION_KILOBOTS ? 2 * a.L.N : a.L.A;
+  const double* act = a.action ? a.action + (size_t)env * A : nullptr;
+  if (a.actionMode == KB_ACTION_KILOBOTS) s.setKilobotActions(act);
+  for (int step = 0; step < a.L.stepsPerAction; ++step) {
+    if (a.actionMode == KB_ACTION_LIGHT && act && a.L.numLights > 0) s.lightStep(act);
+    s.senseControl();
+    s.worldStep();
+  }
+  s.gather(a, env);
+  s.storeState();
+}
+
+template <int LPE>
+__global__ void __launch_bounds__(128) kb_reset_kernel(const __grid_constant__ KernelArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int EPB = 128 / LPE;
+  const int slot = threadIdx.x / LPE;
+  const int env = blockIdx.x * EPB + slot;
+  if (env >= a.numEnvs) return;
+  if (a.mask && !a.mask[env]) return;
+  const Layout& L = a.L;
+  Sim<LPE> s(a.L);
+  s.g.init();
+  s.sm = smem + (size_t)slot * L.smemWords;
+  s.blob = a.blobs + (size_t)env * L.blobWords;
+  const int scene = a.envScene ? a.envScene[env] : 0;
+  s.px = a.proxies + (size_t)scene * L.Pp;
+  s.bc = a.bodies + (size_t)scene * L.Bp;
+  s.lights = a.lights;
+  s.S = L.B;
+  const int lane = s.g.lane;
+  for (int i = lane; i < L.stateWords; i += LPE) s.sm[i] = 0u;
+  s.g.sync();
+  if (lane == 0) {
+    s.hdr(H_NC) = 0u;
+    s.hdr(H_STATUS) = 0u;
+    s.hdr(H_SCENE) = (uint32_t)scene;
+  }
+  // light.__init__ / MomentumLight(velocity=...) / GradientLight(angle=...)
+  if (a.lightInit)
+    for (int i = lane; i < L.L; i += LPE) s.lightState()[i] = a.lightInit[(size_t)env * L.L + i];
+  // controllers: PhototaxisKilobot.__init__ lib/kilobot.py:307-316 (threshold -inf, turn_left)
+  for (int k = lane; k < L.N; k += LPE) {
+    double* c = s.ctrl(k);
+    const int kind = __ldg(&s.bc[L.M + k].kind);
+    c[0] = c[1] = c[2] = c[3] = 0.0;
+    if (kind == KB_KILOBOT_PHOTOTAXIS) {
+      c[0] = __longlong_as_double(0xFFF0000000000000LL);  // -inf
+    } else if ((kind == KB_KILOBOT_VELOCITY || kind == KB_KILOBOT_ACCELERATION) && a.kbVel) {
+      c[0] = a.kbVel[((size_t)env * L.N + k) * 2 + 0];
+      c[1] = a.kbVel[((size_t)env * L.N + k) * 2 + 1];
+    }
+  }
+  // bodies: b2World::CreateBody + CreateFixture (lib/body.py:32-38)
+  for (int b = lane; b < L.B; b += LPE) {
+    const double* p = a.pose + ((size_t)env * L.B + b) * 3;
+    const float x = (float)(25.0 * p[0]);
+    const float y = (float)(25.0 * p[1]);
+    const float ang = (float)p[2];
+    Xf xf;
+    xf.p = mk(x, y);
+    xf.q = rot_set(ang);
+    const V2 lc = mk(__ldg(&s.bc[b].lcx), __ldg(&s.bc[b].lcy));
+    const V2 c = xmul(xf, lc);
+    s.pos4(b) = make_float4(c.x, c.y, ang, 0.0f);
+    s.vel4(b) = make_float4(0.0f, 0.0f, 0.0f, u2f(BF_AWAKE));
+    s.xf4(b) = make_float4(x, y, xf.q.s, xf.q.c);
+  }
+  s.g.sync();
+  s.initScratch();
+  // proxies: b2Fixture::CreateProxies -> fat AABB = aabb +- aabbExtension, buffered as moved
+  uint32_t mlo = 0u, mhi = 0u;
+  const int P = __ldg(&a.scenes[scene].numProxies);
+  for (int p = lane; p < L.P; p += LPE) {
+    if (p >= P) {
+      s.fat4(p) = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);  // unused slot: never overlaps
+      continue;
+    }
+    const int b = __ldg(&s.px[p].body);
+    V2 lo, hi;
+    s.shapeAABB(p, s.bodyXf(b), &lo, &hi);
+    s.fat4(p) = make_float4(lo.x - KB_AABB_EXTENSION, lo.y - KB_AABB_EXTENSION, hi.x + KB_AABB_EXTENSION,
+                            hi.y + KB_AABB_EXTENSION);
+    if (p < 32) mlo |= 1u << p; else mhi |= 1u << (p - 32);
+  }
+  mlo = s.g.red_or(mlo);
+  mhi = s.g.red_or(mhi);
+  if (lane == 0) {
+    s.sm[L.sMoved] = mlo;
+    s.sm[L.sMoved + 1] = mhi;
+  }
+  s.g.sync();
+  s.findNewContacts();  // b2World::Step: m_flags & e_newFixture -> FindNewContacts
+  s.worldStep();        // kilobots_env.py:157 "step to resolve"
+  if (lane == 0 && a.status) a.status[env] = (int32_t)s.hdr(H_STATUS);
+  s.storeState();
+}
+
+// Body.set_pose (lib/body.py:67-69) -> b2Body::SetTransform
+template <int LPE>
+__global__ void __launch_bounds__(128) kb_setpose_kernel(const __grid_constant__ KernelArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int EPB = 128 / LPE;
+  const int slot = threadIdx.x / LPE;
+  const int env = blockIdx.x * EPB + slot;
+  if (env >= a.numEnvs) return;
+  const Layout& L = a.L;
+  Sim<LPE> s(a.L);
+  s.g.init();
+  s.sm = smem + (size_t)slot * L.smemWords;
+  s.blob = a.blobs + (size_t)env * L.blobWords;
+  const int scene = a.envScene ? a.envScene[env] : 0;
+  s.px = a.proxies + (size_t)scene * L.Pp;
+  s.bc = a.bodies + (size_t)scene * L.Bp;
+  s.lights = a.lights;
+  s.S = L.B;
+  s.loadState();
+  s.initScratch();
+  for (int b = s.g.lane; b <= L.B; b += LPE) s.isl(b) = -1;
+  s.g.sync();
+  for (int b = s.g.lane; b < L.B; b += LPE) {
+    const double* p = a.pose + ((size_t)env * L.B + b) * 3;
+    const float x = (float)(p[0] * 25.0);
+    const float y = (float)(p[1] * 25.0);
+    const float ang = (float)p[2];
+    Xf xf;
+    xf.q = rot_set(ang);
+    xf.p = mk(x, y);
+    const float4 k = s.bc4(b);
+    const V2 c = xmul(xf, mk(k.z, k.w));
+    float4 pos = s.pos4(b);
+    pos.x = c.x; pos.y = c.y; pos.z = ang;
+    s.pos4(b) = pos;
+    s.xf4(b) = make_float4(x, y, xf.q.s, xf.q.c);
+    s.sweep4(b) = make_float4(c.x, c.y, ang, 0.0f);
+    reinterpret_cast<float2*>(s.sm + L.sSweep + 4 * (L.B + 1))[b] = make_float2(xf.q.s, xf.q.c);
+    s.isl(b) = 0;
+  }
+  s.g.sync();
+  // SetTransform: Synchronize(xf, xf) with zero displacement.  xf1 == xf2 requires xf1.p == xf.p, which
+  // synchronizeFixtures rebuilds as c0 - q*lc; SetTransform passes m_xf for both, so use toiMode=false
+  // with the saved rotation and accept p = c - q*lc (identical for every body whose xf was synchronised).
+  s.synchronizeFixtures(false);
+  s.storeState();
+}
+
+// ------------------------------------------------------------------------------- host state
+struct Handle {
+  int device = 0;
+  int numEnvs = 0, numScenes = 0;
+  Layout L;
+  std::vector<std::vector<BodyConst>> hostBodies;  // per scene
+  std::vector<int> hostNumProxies;                  // per scene
+  float* dBlobs = nullptr;
+  int32_t* dEnvScene = nullptr;
+  ProxyConst* dProxies = nullptr;
+  BodyConst* dBodies = nullptr;
+  SceneConst* dScenes = nullptr;
+  LightConst* dLights = nullptr;
+  // staging for kb_step_host
+  double* dAction = nullptr;
+  float *dObsK = nullptr, *dObsO = nullptr, *dReward = nullptr;
+  double* dObsL = nullptr;
+  uint8_t* dDone = nullptr;
+  int32_t* dStatus = nullptr;
+  int envsPerBlock = 4;
+  size_t smemBytes = 0;
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail(KB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// --- Box2D fixture preprocessing (float32, same operation order as Box2D) ---------------------
+struct HV2 {
+  float x, y;
+};
+static inline HV2 hv(float x, float y) { return HV2{x, y}; }
+static inline HV2 operator+(HV2 a, HV2 b) { return hv(a.x + b.x, a.y + b.y); }
+static inline HV2 operator-(HV2 a, HV2 b) { return hv(a.x - b.x, a.y - b.y); }
+static inline HV2 operator*(float s, HV2 a) { return hv(s * a.x, s * a.y); }
+static inline float hdot(HV2 a, HV2 b) { return a.x * b.x + a.y * b.y; }
+static inline float hcross(HV2 a, HV2 b) { return a.x * b.y - a.y * b.x; }
+
+// b2PolygonShape::Set: weld, gift-wrap from the right-most vertex, normals, centroid
+static bool buildPolygon(const KbFixtureDef& fd, ProxyConst* pc) {
+  const float linearSlop = 0.005f;
+  int n = std::min(fd.vertex_count, (int)KB_MAX_POLY_VERTS);
+  HV2 ps[KB_MAX_POLY_VERTS];
+  int tempCount = 0;
+  for (int i = 0; i < n; ++i) {
+    HV2 v = hv(fd.vx[i], fd.vy[i]);
+    bool unique = true;
+    for (int j = 0; j < tempCount; ++j) {
+      HV2 d = v - ps[j];
+      if (hdot(d, d) < 0.5f * linearSlop) {
+        unique = false;
+        break;
+      }
+    }
+    if (unique) ps[tempCount++] = v;
+  }
+  n = tempCount;
+  if (n < 3) return false;
+  int i0 = 0;
+  float x0 = ps[0].x;
+  for (int i = 1; i < n; ++i) {
+    float x = ps[i].x;
+    if (x > x0 || (x == x0 && ps[i].y < ps[i0].y)) {
+      i0 = i;
+      x0 = x;
+    }
+  }
+  int hull[KB_MAX_POLY_VERTS];
+  int m = 0;
+  int ih = i0;
+  for (;;) {
+    hull[m] = ih;
+    int ie = 0;
+    for (int j = 1; j < n; ++j) {
+      if (ie == ih) {
+        ie = j;
+        continue;
+      }
+      HV2 r = ps[ie] - ps[hull[m]];
+      HV2 v = ps[j] - ps[hull[m]];
+      float c = hcross(r, v);
+      if (c < 0.0f) ie = j;
+      if (c == 0.0f && hdot(v, v) > hdot(r, r)) ie = j;
+    }
+    ++m;
+    ih = ie;
+    if (ie == i0) break;
+  }
+  pc->count = m;
+  for (int i = 0; i < m; ++i) {
+    pc->vx[i] = ps[hull[i]].x;
+    pc->vy[i] = ps[hull[i]].y;
+  }
+  for (int i = 0; i < m; ++i) {
+    int i2 = i + 1 < m ? i + 1 : 0;
+    HV2 edge = hv(pc->vx[i2], pc->vy[i2]) - hv(pc->vx[i], pc->vy[i]);
+    // b2Cross(edge, 1) then Normalize
+    HV2 nrm = hv(1.0f * edge.y, -1.0f * edge.x);
+    float len = sqrtf(nrm.x * nrm.x + nrm.y * nrm.y);
+    if (!(len < FLT_EPSILON)) {
+      float inv = 1.0f / len;
+      nrm.x *= inv;
+      nrm.y *= inv;
+    }
+    pc->nx[i] = nrm.x;
+    pc->ny[i] = nrm.y;
+  }
+  // ComputeCentroid (reference point at the origin)
+  HV2 c = hv(0.0f, 0.0f);
+  float area = 0.0f;
+  const float inv3 = 1.0f / 3.0f;
+  for (int i = 0; i < m; ++i) {
+    HV2 p1 = hv(0.0f, 0.0f);
+    HV2 p2 = hv(pc->vx[i], pc->vy[i]);
+    HV2 p3 = i + 1 < m ? hv(pc->vx[i + 1], pc->vy[i + 1]) : hv(pc->vx[0], pc->vy[0]);
+    HV2 e1 = p2 - p1;
+    HV2 e2 = p3 - p1;
+    float D = hcross(e1, e2);
+    float triangleArea = 0.5f * D;
+    area += triangleArea;
+    c = c + (triangleArea * inv3) * ((p1 + p2) + p3);
+  }
+  c = (1.0f / area) * c;
+  pc->cx = c.x;
+  pc->cy = c.y;
+  return true;
+}
+
+static void buildBox(float hx, float hy, ProxyConst* pc) {
+  pc->count = 4;
+  const float vx[4] = {-hx, hx, hx, -hx}, vy[4] = {-hy, -hy, hy, hy};
+  const float nx[4] = {0.0f, 1.0f, 0.0f, -1.0f}, ny[4] = {-1.0f, 0.0f, 1.0f, 0.0f};
+  for (int i = 0; i < 4; ++i) {
+    pc->vx[i] = vx[i];
+    pc->vy[i] = vy[i];
+    pc->nx[i] = nx[i];
+    pc->ny[i] = ny[i];
+  }
+  pc->cx = 0.0f;
+  pc->cy = 0.0f;
+}
+
+// b2Shape::ComputeMass
+static void fixtureMass(const ProxyConst& pc, float density, float* mass, HV2* center, float* I) {
+  const float b2pi = 3.14159265359f;
+  if (pc.type == SHAPE_CIRCLE) {
+    *mass = density * b2pi * pc.radius * pc.radius;
+    *center = hv(0.0f, 0.0f);
+    *I = *mass * (0.5f * pc.radius * pc.radius + hdot(*center, *center));
+    return;
+  }
+  HV2 ctr = hv(0.0f, 0.0f);
+  float area = 0.0f, inertia = 0.0f;
+  HV2 s = hv(0.0f, 0.0f);
+  for (int i = 0; i < pc.count; ++i) s = s + hv(pc.vx[i], pc.vy[i]);
+  s = (1.0f / pc.count) * s;
+  const float k_inv3 = 1.0f / 3.0f;
+  for (int i = 0; i < pc.count; ++i) {
+    HV2 e1 = hv(pc.vx[i], pc.vy[i]) - s;
+    HV2 e2 = i + 1 < pc.count ? hv(pc.vx[i + 1], pc.vy[i + 1]) - s : hv(pc.vx[0], pc.vy[0]) - s;
+    float D = hcross(e1, e2);
+    float triangleArea = 0.5f * D;
+    area += triangleArea;
+    ctr = ctr + (triangleArea * k_inv3) * (e1 + e2);
+    float ex1 = e1.x, ey1 = e1.y, ex2 = e2.x, ey2 = e2.y;
+    float intx2 = ex1 * ex1 + ex2 * ex1 + ex2 * ex2;
+    float inty2 = ey1 * ey1 + ey2 * ey1 + ey2 * ey2;
+    inertia += (0.25f * k_inv3 * D) * (intx2 + inty2);
+  }
+  *mass = density * area;
+  ctr = (1.0f / area) * ctr;
+  *center = ctr + s;
+  *I = density * inertia;
+  *I += *mass * (hdot(*center, *center) - hdot(ctr, ctr));
+}
+
+static int lightStateDim(int type) { return type == KB_LIGHT_MOMENTUM ? 4 : (type == KB_LIGHT_LINEAR ? 1 : 2); }
+static int lightActionDim(int type) { return type == KB_LIGHT_LINEAR ? 1 : 2; }
+static int round4(int x) { return (x + 3) & ~3; }
+
+static int buildScene(const KbSceneDesc& sd, int Bp, int Pp, std::vector<ProxyConst>* proxies,
+                      std::vector<BodyConst>* bodies, SceneConst* sc) {
+  const int B = sd.num_bodies;
+  proxies->assign(Pp, ProxyConst());
+  bodies->assign(Bp, BodyConst());
+  std::memset(proxies->data(), 0, sizeof(ProxyConst) * Pp);
+  std::memset(bodies->data(), 0, sizeof(BodyConst) * Bp);
+  int p = 0;
+  // table chain, kilobots_env.py:46-51: (x0,y1) -> (x0,y0) -> (x1,y0) -> (x1,y1) [-> (x0,y1)]
+  if (sd.wall_edges != 0 && sd.wall_edges != 3 && sd.wall_edges != 4) return fail(KB_ERR_INVALID, "wall_edges must be 0, 3 or 4");
+  {
+    const float vx[5] = {sd.wall_x0, sd.wall_x0, sd.wall_x1, sd.wall_x1, sd.wall_x0};
+    const float vy[5] = {sd.wall_y1, sd.wall_y0, sd.wall_y0, sd.wall_y1, sd.wall_y1};
+    const bool loop = sd.wall_edges == 4;
+    const int count = loop ? 5 : 4;
+    for (int i = 0; i < sd.wall_edges; ++i) {
+      ProxyConst& pc = (*proxies)[p++];
+      pc.body = B;  // static slot
+      pc.type = SHAPE_EDGE;
+      pc.radius = 2.0f * 0.005f;
+      pc.friction = sd.wall_friction;
+      pc.restitution = 0.0f;
+      pc.vx[1] = vx[i]; pc.vy[1] = vy[i];
+      pc.vx[2] = vx[i + 1]; pc.vy[2] = vy[i + 1];
+      if (i > 0) { pc.vx[0] = vx[i - 1]; pc.vy[0] = vy[i - 1]; pc.has0 = 1; }
+      else if (loop) { pc.vx[0] = vx[count - 2]; pc.vy[0] = vy[count - 2]; pc.has0 = 1; }
+      if (i < count - 2) { pc.vx[3] = vx[i + 2]; pc.vy[3] = vy[i + 2]; pc.has3 = 1; }
+      else if (loop) { pc.vx[3] = vx[1]; pc.vy[3] = vy[1]; pc.has3 = 1; }
+    }
+  }
+  for (int b = 0; b < B; ++b) {
+    const KbBodyDef& bd = sd.bodies[b];
+    BodyConst& bcst = (*bodies)[b];
+    if (bd.num_fixtures < 1 || bd.num_fixtures > KB_MAX_FIXTURES) return fail(KB_ERR_INVALID, "body needs 1..3 fixtures");
+    bcst.kind = bd.kind;
+    bcst.firstProxy = p;
+    bcst.numProxies = bd.num_fixtures;
+    bcst.linearDamping = bd.linear_damping;
+    bcst.angularDamping = bd.angular_damping;
+    // SimplePhototaxisKilobot.step sets linearDamping = 0 on every call (lib/kilobot.py:203); the only
+    // step that runs before the first call is reset's settle step, where the velocity is zero.
+    if (bd.kind == KB_KILOBOT_SIMPLE_PHOTOTAXIS) bcst.linearDamping = 0.0f;
+    for (int f = 0; f < bd.num_fixtures; ++f) {
+      const KbFixtureDef& fd = bd.fixtures[f];
+      ProxyConst& pc = (*proxies)[p++];
+      pc.body = b;
+      pc.friction = fd.friction;
+      pc.restitution = fd.restitution;
+      if (fd.shape == KB_SHAPE_CIRCLE) {
+        pc.type = SHAPE_CIRCLE;
+        pc.radius = fd.radius;
+      } else if (fd.shape == KB_SHAPE_BOX) {
+        pc.type = SHAPE_POLYGON;
+        pc.radius = 2.0f * 0.005f;
+        buildBox(fd.hx, fd.hy, &pc);
+      } else if (fd.shape == KB_SHAPE_POLYGON) {
+        pc.type = SHAPE_POLYGON;
+        pc.radius = 2.0f * 0.005f;
+        if (!buildPolygon(fd, &pc)) return fail(KB_ERR_INVALID, "degenerate polygon fixture");
+      } else {
+        return fail(KB_ERR_INVALID, "unknown fixture shape");
+      }
+    }
+    // b2Body::ResetMassData: fixtures are visited newest first (m_fixtureList is LIFO)
+    float mass = 0.0f, I = 0.0f;
+    HV2 lc = hv(0.0f, 0.0f);
+    for (int f = bd.num_fixtures - 1; f >= 0; --f) {
+      const float density = bd.fixtures[f].density;
+      if (density == 0.0f) continue;
+      float m, i;
+      HV2 c;
+      fixtureMass((*proxies)[bcst.firstProxy + f], density, &m, &c, &i);
+      mass += m;
+      lc = lc + m * c;
+      I += i;
+    }
+    float invMass, invI;
+    if (mass > 0.0f) {
+      invMass = 1.0f / mass;
+      lc = invMass * lc;
+    } else {
+      mass = 1.0f;
+      invMass = 1.0f;
+    }
+    if (I > 0.0f) {
+      I -= mass * hdot(lc, lc);
+      invI = 1.0f / I;
+    } else {
+      invI = 0.0f;
+    }
+    bcst.invMass = invMass;
+    bcst.invI = invI;
+    bcst.lcx = lc.x;
+    bcst.lcy = lc.y;
+  }
+  sc->numProxies = p;
+  sc->wallEdges = sd.wall_edges;
+  sc->rewardConst = sd.reward_const;
+  return KB_OK;
+}
+
+static void fillArgs(const Handle* h, KernelArgs* a) {
+  std::memset(a, 0, sizeof(*a));
+  a->L = h->L;
+  a->blobs = h->dBlobs;
+  a->envScene = h->dEnvScene;
+  a->proxies = h->dProxies;
+  a->bodies = h->dBodies;
+  a->scenes = h->dScenes;
+  a->lights = h->dLights;
+  a->numEnvs = h->numEnvs;
+}
+
+}  // namespace kb
+
+using namespace kb;
+
+extern "C" {
+
+const char* kb_last_error(void) { return g_err.c_str(); }
+
+int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_scene, int32_t num_envs,
+              int32_t max_contacts, int32_t device, KbHandle** out) {
+  if (!scenes || num_scenes < 1 || num_envs < 1 || !out) return fail(KB_ERR_INVALID, "kb_create: invalid arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(KB_ERR_NO_DEVICE, "kb_create: no CUDA device (this library has no CPU fallback)");
+  }
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(KB_ERR_NO_DEVICE, "kb_create: device is not sm_100 (B200); no fallback path exists");
+  CUDA_TRY(cudaSetDevice(device));
+
+  const KbSceneDesc& s0 = scenes[0];
+  const int B = s0.num_bodies, M = s0.num_objects, N = B - M;
+  if (B < 1 || M < 0 || N < 0) return fail(KB_ERR_INVALID, "kb_create: bad body counts");
+  if (B > KB_MAX_BODIES) return fail(KB_ERR_CAPACITY, "kb_create: more than 63 bodies per env is not supported by the warp-per-env kernel");
+  if (s0.num_lights > KB_MAX_LIGHTS) return fail(KB_ERR_INVALID, "kb_create: too many lights");
+  int P = 0;
+  for (int s = 0; s < num_scenes; ++s) {
+    const KbSceneDesc& sd = scenes[s];
+    if (sd.num_bodies != B || sd.num_objects != M || sd.num_lights != s0.num_lights ||
+        sd.steps_per_action != s0.steps_per_action || sd.velocity_iterations != s0.velocity_iterations ||
+        sd.position_iterations != s0.position_iterations || sd.dt != s0.dt || sd.damping_mode != s0.damping_mode ||
+        sd.enable_toi != s0.enable_toi || sd.enable_sleep != s0.enable_sleep)
+      return fail(KB_ERR_INVALID, "kb_create: scenes must agree in body/light counts and simulation constants");
+    int p = sd.wall_edges;
+    for (int b = 0; b < B; ++b) {
+      p += sd.bodies[b].num_fixtures;
+      if (sd.bodies[b].kind != s0.bodies[b].kind) return fail(KB_ERR_INVALID, "kb_create: scenes must agree in body kinds");
+    }
+    P = std::max(P, p);
+  }
+  if (P > KB_MAX_PROXIES) return fail(KB_ERR_CAPACITY, "kb_create: more than 64 proxies per env is not supported");
+
+  Handle* h = new Handle();
+  h->device = device;
+  h->numEnvs = num_envs;
+  h->numScenes = num_scenes;
+  Layout& L = h->L;
+  std::memset(&L, 0, sizeof(L));
+  L.B = B; L.M = M; L.N = N; L.P = P;
+  L.Bp = B + 1;
+  L.Pp = P;
+  L.Cmax = round4(max_contacts > 0 ? max_contacts : std::min(P * (P - 1) / 2, 8 * B + 32));
+  L.Kmax = round4(std::min(L.Cmax, std::max(16, 3 * B + 16)));
+  L.numLights = s0.num_lights;
+  for (int l = 0; l < s0.num_lights; ++l) {
+    L.L += lightStateDim(s0.lights[l].type);
+    L.A += lightActionDim(s0.lights[l].type);
+  }
+  int o = 0;
+  L.oHdr = o; o += 8;
+  L.oCnt = o; o += 2 * KB_NUM_COUNTERS;
+  L.oLight = o; o += round4(2 * std::max(L.L, 1));
+  L.oCtrl = o; o += round4(8 * std::max(N, 1));
+  L.oPos = o; o += 4 * L.Bp;
+  L.oVel = o; o += 4 * L.Bp;
+  L.oXf = o; o += 4 * L.Bp;
+  L.oFat = o; o += 4 * L.Pp;
+  L.oPair = o; o += L.Cmax;
+  L.oInfo = o; o += L.Cmax;
+  L.stateWords = round4(o);
+  L.oMan = L.stateWords;
+  L.blobWords = L.stateWords + MR_WORDS * L.Cmax;
+  o = L.stateWords;
+  L.sSweep = o; o += round4(6 * L.Bp);
+  L.sBc = o; o += 4 * L.Bp;
+  L.sIsl = o; o += round4(L.Bp);
+  L.sIslMin = o; o += round4(L.Bp);
+  L.sStack = o; o += round4(L.Bp);
+  L.sLastLvl = o; o += round4(L.Bp);
+  L.sAdj = o; o += round4(2 * L.Pp);
+  L.sMoved = L.oHdr + 4;  // persistent: SetTransform may buffer moves between steps
+  L.sTlist = o; o += L.Kmax;
+  L.sOrder = o; o += 2 * L.Kmax;
+  L.sLvl = o; o += L.Kmax;
+  L.sLvlOff = o; o += round4(2 * (L.Kmax + 2));
+  L.sEslot = o; o += L.Kmax;
+  L.sPool = o; o += POOL_FIELDS * L.Kmax;
+  L.sToi = o; o += L.Cmax;
+  L.sMisc = o; o += 8;
+  L.smemWords = round4(o);
+  L.stepsPerAction = s0.steps_per_action;
+  L.velIters = s0.velocity_iterations;
+  L.posIters = s0.position_iterations;
+  L.dampingMode = s0.damping_mode;
+  L.enableToi = s0.enable_toi;
+  L.enableSleep = s0.enable_sleep;
+  L.dt = s0.dt;
+  {
+    // Kilobot.step single-motor branches, lib/kilobot.py:103-121 (float64, then b2Vec2 float32)
+    const double legLeft[2] = {-0.013, -0.009}, legRight[2] = {+0.013, -0.009};
+    const double maxAngular = 0.5 * M_PI, dt = 1. / 10;
+    double av = 255 / 255. * maxAngular, ad = av * dt;
+    double c = std::cos(ad), s = std::sin(ad);
+    L.transRight[0] = (float)((legLeft[0] - (c * legLeft[0] + (-s) * legLeft[1])) * 25.0);
+    L.transRight[1] = (float)((legLeft[1] - (s * legLeft[0] + c * legLeft[1])) * 25.0);
+    L.omegaRight = (float)av;
+    av = -255 / 255. * maxAngular;
+    ad = av * dt;
+    c = std::cos(ad);
+    s = std::sin(ad);
+    L.transLeft[0] = (float)((legRight[0] - (c * legRight[0] + (-s) * legRight[1])) * 25.0);
+    L.transLeft[1] = (float)((legRight[1] - (s * legRight[0] + c * legRight[1])) * 25.0);
+    L.omegaLeft = (float)av;
+  }
+  h->envsPerBlock = 4;
+  h->smemBytes = (size_t)h->envsPerBlock * L.smemWords * 4;
+  if (h->smemBytes > (size_t)prop.sharedMemPerBlockOptin) {
+    delete h;
+    return fail(KB_ERR_CAPACITY, "kb_create: per-env shared-memory image too large; lower max_contacts");
+  }
+
+  std::vector<ProxyConst> allProxies;
+  std::vector<BodyConst> allBodies;
+  std::vector<SceneConst> allScenes(num_scenes);
+  h->hostBodies.resize(num_scenes);
+  for (int s = 0; s < num_scenes; ++s) {
+    std::vector<ProxyConst> px;
+    int rc = buildScene(scenes[s], L.Bp, L.Pp, &px, &h->hostBodies[s], &allScenes[s]);
+    if (rc != KB_OK) {
+      delete h;
+      return rc;
+    }
+    allProxies.insert(allProxies.end(), px.begin(), px.end());
+    h->hostNumProxies.push_back(allScenes[s].numProxies);
+    allBodies.insert(allBodies.end(), h->hostBodies[s].begin(), h->hostBodies[s].end());
+  }
+  std::vector<LightConst> lights(std::max(1, (int)s0.num_lights));
+  for (int l = 0; l < s0.num_lights; ++l) {
+    const KbLightDef& ld = s0.lights[l];
+    LightConst& lc = lights[l];
+    lc.type = ld.type;
+    lc.relative = ld.relative_actions;
+    lc.radius = ld.radius;
+    for (int k = 0; k < 2; ++k) {
+      lc.blo[k] = ld.bounds_lo[k];
+      lc.bhi[k] = ld.bounds_hi[k];
+      lc.alo[k] = ld.action_lo[k];
+      lc.ahi[k] = ld.action_hi[k];
+    }
+    lc.maxVel = ld.max_velocity;
+  }
+#define ALLOC_COPY(dst, vec)                                                                   \
+  CUDA_TRY(cudaMalloc(&(dst), sizeof((vec)[0]) * (vec).size()));                               \
+  CUDA_TRY(cudaMemcpy((dst), (vec).data(), sizeof((vec)[0]) * (vec).size(), cudaMemcpyHostToDevice));
+  ALLOC_COPY(h->dProxies, allProxies);
+  ALLOC_COPY(h->dBodies, allBodies);
+  ALLOC_COPY(h->dScenes, allScenes);
+  ALLOC_COPY(h->dLights, lights);
+#undef ALLOC_COPY
+  if (env_scene) {
+    for (int i = 0; i < num_envs; ++i)
+      if (env_scene[i] < 0 || env_scene[i] >= num_scenes) return fail(KB_ERR_INVALID, "kb_create: env_scene out of range");
+    CUDA_TRY(cudaMalloc(&h->dEnvScene, sizeof(int32_t) * num_envs));
+    CUDA_TRY(cudaMemcpy(h->dEnvScene, env_scene, sizeof(int32_t) * num_envs, cudaMemcpyHostToDevice));
+  }
+  const size_t blobBytes = (size_t)num_envs * L.blobWords * 4;
+  CUDA_TRY(cudaMalloc(&h->dBlobs, blobBytes));
+  CUDA_TRY(cudaMemset(h->dBlobs, 0, blobBytes));
+  const int Amax = std::max(std::max(L.A, 2 * N), 1);
+  CUDA_TRY(cudaMalloc(&h->dAction, sizeof(double) * (size_t)num_envs * Amax));
+  CUDA_TRY(cudaMalloc(&h->dObsK, sizeof(float) * (size_t)num_envs * std::max(N, 1) * 3));
+  CUDA_TRY(cudaMalloc(&h->dObsO, sizeof(float) * (size_t)num_envs * std::max(M, 1) * 3));
+  CUDA_TRY(cudaMalloc(&h->dObsL, sizeof(double) * (size_t)num_envs * std::max(L.L, 1)));
+  CUDA_TRY(cudaMalloc(&h->dReward, sizeof(float) * num_envs));
+  CUDA_TRY(cudaMalloc(&h->dDone, num_envs));
+  CUDA_TRY(cudaMalloc(&h->dStatus, sizeof(int32_t) * num_envs));
+  CUDA_TRY(cudaFuncSetAttribute(kb_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(kb_reset_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(kb_setpose_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+  *out = reinterpret_cast<KbHandle*>(h);
+  return KB_OK;
+}
+
+int kb_destroy(KbHandle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return KB_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->dBlobs); cudaFree(h->dEnvScene); cudaFree(h->dProxies); cudaFree(h->dBodies);
+  cudaFree(h->dScenes); cudaFree(h->dLights); cudaFree(h->dAction); cudaFree(h->dObsK); cudaFree(h->dObsO);
+  cudaFree(h->dObsL); cudaFree(h->dReward); cudaFree(h->dDone); cudaFree(h->dStatus);
+  delete h;
+  return KB_OK;
+}
+
+int kb_get_dims(const KbHandle* hh, KbDims* d) {
+  const Handle* h = reinterpret_cast<const Handle*>(hh);
+  if (!h || !d) return fail(KB_ERR_INVALID, "kb_get_dims: null");
+  d->num_envs = h->numEnvs;
+  d->num_bodies = h->L.B;
+  d->num_objects = h->L.M;
+  d->num_kilobots = h->L.N;
+  d->num_proxies = h->L.P;
+  d->max_contacts = h->L.Cmax;
+  d->light_state_dim = h->L.L;
+  d->action_dim = h->L.A;
+  d->state_bytes_per_env = h->L.blobWords * 4;
+  return KB_OK;
+}
+
+static int launchGrid(const Handle* h) { return (h->numEnvs + h->envsPerBlock - 1) / h->envsPerBlock; }
+
+int kb_reset(KbHandle* hh, const uint8_t* mask, const double* body_pose, const double* light_state,
+             const double* kb_velocity, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !body_pose) return fail(KB_ERR_INVALID, "kb_reset: null handle or poses");
+  if (h->L.L > 0 && !light_state) return fail(KB_ERR_INVALID, "kb_reset: light_state required");
+  CUDA_TRY(cudaSetDevice(h->device));
+  KernelArgs a;
+  fillArgs(h, &a);
+  a.mask = mask;
+  a.pose = body_pose;
+  a.lightInit = light_state;
+  a.kbVel = kb_velocity;
+  a.status = h->dStatus;
+  kb_reset_kernel<32><<<launchGrid(h), 128, h->smemBytes, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return KB_OK;
+}
+
+int kb_step(KbHandle* hh, const double* action, int32_t action_mode, float* obs_kilobots, float* obs_objects,
+            double* obs_light, float* reward, uint8_t* done, int32_t* status, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(KB_ERR_INVALID, "kb_step: null handle");
+  if (action_mode != KB_ACTION_NONE && action_mode != KB_ACTION_LIGHT && action_mode != KB_ACTION_KILOBOTS)
+    return fail(KB_ERR_INVALID, "kb_step: bad action_mode");
+  CUDA_TRY(cudaSetDevice(h->device));
+  KernelArgs a;
+  fillArgs(h, &a);
+  a.action = action_mode == KB_ACTION_NONE ? nullptr : action;
+  a.actionMode = a.action || action_mode == KB_ACTION_KILOBOTS ? action_mode : KB_ACTION_NONE;
+  a.obsKilobots = obs_kilobots;
+  a.obsObjects = obs_objects;
+  a.obsLight = obs_light;
+  a.reward = reward;
+  a.done = done;
+  a.status = status;
+  kb_step_kernel<32><<<launchGrid(h), 128, h->smemBytes, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return KB_OK;
+}
+
+int kb_step_host(KbHandle* hh, const double* action, int32_t action_mode, float* obs_kilobots, float* obs_objects,
+                 double* obs_light, float* reward, uint8_t* done, int32_t* status, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(KB_ERR_INVALID, "kb_step_host: null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layout& L = h->L;
+  const size_t E = (size_t)h->numEnvs;
+  const double* dAct = nullptr;
+  if (action && action_mode != KB_ACTION_NONE) {
+    const size_t A = action_mode == KB_ACTION_KILOBOTS ? 2 * (size_t)L.N : (size_t)L.A;
+    CUDA_TRY(cudaMemcpyAsync(h->dAction, action, sizeof(double) * E * A, cudaMemcpyHostToDevice, st));
+    dAct = h->dAction;
+  }
+  int rc = kb_step(hh, dAct, action_mode, obs_kilobots ? h->dObsK : nullptr, obs_objects ? h->dObsO : nullptr,
+                   obs_light ? h->dObsL : nullptr, reward ? h->dReward : nullptr, done ? h->dDone : nullptr,
+                   status ? h->dStatus : nullptr, stream);
+  if (rc != KB_OK) return rc;
+  if (obs_kilobots) CUDA_TRY(cudaMemcpyAsync(obs_kilobots, h->dObsK, sizeof(float) * E * L.N * 3, cudaMemcpyDeviceToHost, st));
+  if (obs_objects && L.M > 0) CUDA_TRY(cudaMemcpyAsync(obs_objects, h->dObsO, sizeof(float) * E * L.M * 3, cudaMemcpyDeviceToHost, st));
+  if (obs_light && L.L > 0) CUDA_TRY(cudaMemcpyAsync(obs_light, h->dObsL, sizeof(double) * E * L.L, cudaMemcpyDeviceToHost, st));
+  if (reward) CUDA_TRY(cudaMemcpyAsync(reward, h->dReward, sizeof(float) * E, cudaMemcpyDeviceToHost, st));
+  if (done) CUDA_TRY(cudaMemcpyAsync(done, h->dDone, E, cudaMemcpyDeviceToHost, st));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, h->dStatus, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return KB_OK;
+}
+
+// ---- introspection (host pointers, synchronous) ------------------------------------------------
+static int fetchBlobs(Handle* h, std::vector<uint32_t>* buf) {
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  buf->resize((size_t)h->numEnvs * h->L.blobWords);
+  CUDA_TRY(cudaMemcpy(buf->data(), h->dBlobs, buf->size() * 4, cudaMemcpyDeviceToHost));
+  return KB_OK;
+}
+static inline float asf(uint32_t u) {
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+int kb_get_bodies(KbHandle* hh, float* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::vector<uint32_t> buf;
+  int rc = fetchBlobs(h, &buf);
+  if (rc) return rc;
+  const Layout& L = h->L;
+  for (int e = 0; e < h->numEnvs; ++e) {
+    const uint32_t* w = buf.data() + (size_t)e * L.blobWords;
+    for (int b = 0; b < L.B; ++b) {
+      float* o = out + ((size_t)e * L.B + b) * KB_BODY_STATE_FLOATS;
+      const uint32_t* pos = w + L.oPos + 4 * b;
+      const uint32_t* vel = w + L.oVel + 4 * b;
+      const uint32_t* xf = w + L.oXf + 4 * b;
+      o[0] = asf(pos[0]); o[1] = asf(pos[1]); o[2] = asf(pos[2]);
+      o[3] = asf(vel[0]); o[4] = asf(vel[1]); o[5] = asf(vel[2]);
+      o[6] = asf(pos[3]);
+      o[7] = (vel[3] & BF_AWAKE) ? 1.0f : 0.0f;
+      o[8] = asf(xf[0]); o[9] = asf(xf[1]); o[10] = asf(xf[2]); o[11] = asf(xf[3]);
+    }
+  }
+  return KB_OK;
+}
+
+int kb_set_poses(KbHandle* hh, const double* body_pose) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !body_pose) return fail(KB_ERR_INVALID, "kb_set_poses: null");
+  CUDA_TRY(cudaSetDevice(h->device));
+  double* d = nullptr;
+  const size_t bytes = sizeof(double) * (size_t)h->numEnvs * h->L.B * 3;
+  CUDA_TRY(cudaMalloc(&d, bytes));
+  CUDA_TRY(cudaMemcpy(d, body_pose, bytes, cudaMemcpyHostToDevice));
+  KernelArgs a;
+  fillArgs(h, &a);
+  a.pose = d;
+  kb_setpose_kernel<32><<<launchGrid(h), 128, h->smemBytes>>>(a);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(KB_ERR_CUDA, cudaGetErrorString(e));
+  return KB_OK;
+}
+
+int kb_get_contacts(KbHandle* hh, int32_t* pairs, int32_t* count) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::vector<uint32_t> buf;
+  int rc = fetchBlobs(h, &buf);
+  if (rc) return rc;
+  const Layout& L = h->L;
+  for (int e = 0; e < h->numEnvs; ++e) {
+    const uint32_t* w = buf.data() + (size_t)e * L.blobWords;
+    const int nC = (int)w[L.oHdr + H_NC];
+    count[e] = nC;
+    for (int k = 0; k < nC && k < L.Cmax; ++k) {
+      const int i = nC - 1 - k;  // world-list order: newest first
+      const uint32_t pr = w[L.oPair + i], info = w[L.oInfo + i];
+      int32_t* o = pairs + ((size_t)e * L.Cmax + k) * 4;
+      o[0] = (int32_t)(pr & 0xFFFF);
+      o[1] = (int32_t)(pr >> 16);
+      o[2] = (info & CI_TOUCHING) ? 1 : 0;
+      o[3] = (int32_t)((info & CI_PC_MASK) >> CI_PC_SHIFT);
+    }
+  }
+  return KB_OK;
+}
+
+int kb_get_impulses(KbHandle* hh, float* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::vector<uint32_t> buf;
+  int rc = fetchBlobs(h, &buf);
+  if (rc) return rc;
+  const Layout& L = h->L;
+  for (int e = 0; e < h->numEnvs; ++e) {
+    const uint32_t* w = buf.data() + (size_t)e * L.blobWords;
+    const int nC = (int)w[L.oHdr + H_NC];
+    for (int k = 0; k < nC && k < L.Cmax; ++k) {
+      const int i = nC - 1 - k;
+      const uint32_t info = w[L.oInfo + i];
+      const int pc = (int)((info & CI_PC_MASK) >> CI_PC_SHIFT);
+      const uint32_t* rec = w + L.oMan + MR_WORDS * i;
+      float* o = out + ((size_t)e * L.Cmax + k) * 4;
+      o[0] = pc > 0 ? asf(rec[MR_P0N]) : 0.0f;
+      o[1] = pc > 0 ? asf(rec[MR_P0T]) : 0.0f;
+      o[2] = pc > 1 ? asf(rec[MR_P1N]) : 0.0f;
+      o[3] = pc > 1 ? asf(rec[MR_P1T]) : 0.0f;
+    }
+  }
+  return KB_OK;
+}
+
+int kb_get_counters(KbHandle* hh, uint64_t* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::vector<uint32_t> buf;
+  int rc = fetchBlobs(h, &buf);
+  if (rc) return rc;
+  const Layout& L = h->L;
+  for (int e = 0; e < h->numEnvs; ++e) {
+    const uint32_t* w = buf.data() + (size_t)e * L.blobWords;
+    std::memcpy(out + (size_t)e * KB_NUM_COUNTERS, w + L.oCnt, sizeof(uint64_t) * KB_NUM_COUNTERS);
+  }
+  return KB_OK;
+}
+
+int kb_get_proxies(KbHandle* hh, float* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::vector<uint32_t> buf;
+  int rc = fetchBlobs(h, &buf);
+  if (rc) return rc;
+  const Layout& L = h->L;
+  for (int e = 0; e < h->numEnvs; ++e) {
+    const uint32_t* w = buf.data() + (size_t)e * L.blobWords;
+    const int np = h->hostNumProxies[w[L.oHdr + H_SCENE]];
+    std::memset(out + (size_t)e * L.P * 4, 0, sizeof(float) * 4 * L.P);
+    std::memcpy(out + (size_t)e * L.P * 4, w + L.oFat, sizeof(float) * 4 * np);
+  }
+  return KB_OK;
+}
+
+int kb_get_controllers(KbHandle* hh, double* ctrl, double* light) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  std::vector<uint32_t> buf;
+  int rc = fetchBlobs(h, &buf);
+  if (rc) return rc;
+  const Layout& L = h->L;
+  for (int e = 0; e < h->numEnvs; ++e) {
+    const uint32_t* w = buf.data() + (size_t)e * L.blobWords;
+    if (ctrl) std::memcpy(ctrl + (size_t)e * L.N * 4, w + L.oCtrl, sizeof(double) * 4 * L.N);
+    if (light) std::memcpy(light + (size_t)e * L.L, w + L.oLight, sizeof(double) * L.L);
+  }
+  return KB_OK;
+}
+
+int kb_get_state(KbHandle* hh, void* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !out) return fail(KB_ERR_INVALID, "kb_get_state: null");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, h->dBlobs, (size_t)h->numEnvs * h->L.blobWords * 4, cudaMemcpyDeviceToHost));
+  return KB_OK;
+}
+
+int kb_set_state(KbHandle* hh, const void* in) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !in) return fail(KB_ERR_INVALID, "kb_set_state: null");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(h->dBlobs, in, (size_t)h->numEnvs * h->L.blobWords * 4, cudaMemcpyHostToDevice));
+  return KB_OK;
+}
+
+int kb_get_mass_data(KbHandle* hh, float* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !out) return fail(KB_ERR_INVALID, "kb_get_mass_data: null");
+  for (int s = 0; s < h->numScenes; ++s)
+    for (int b = 0; b < h->L.B; ++b) {
+      const BodyConst& bc = h->hostBodies[s][b];
+      float* o = out + ((size_t)s * h->L.B + b) * 4;
+      o[0] = bc.invMass; o[1] = bc.invI; o[2] = bc.lcx; o[3] = bc.lcy;
+    }
+  return KB_OK;
+}
+
+}  // extern "C"

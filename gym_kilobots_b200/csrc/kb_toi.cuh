@@ -1,0 +1,690 @@
+// kb_toi.cuh -- continuous collision against the static table: GPU restatement of Box2D 2.3.x
+// b2Distance (GJK + simplex cache), b2TimeOfImpact (conservative advancement) and
+// b2World::SolveTOI / b2Island::SolveTOI, reached from b2World.Step at
+// gym_kilobots/envs/kilobots_env.py:187.  There are no bullets, so only dynamic-vs-table contacts
+// are candidates.  One lane evaluates one candidate contact's time of impact; the (rare) TOI event
+// itself -- a mini island of one dynamic body and its wall contacts -- is solved by lane 0.
+#pragma once
+#include "kb_step.cuh"
+
+namespace kb {
+
+struct SweepD {
+  V2 lc, c0, c;
+  float a0, a, alpha0;
+};
+__device__ __forceinline__ Xf sweep_xf(const SweepD& s, float beta) {
+  Xf xf;
+  xf.p = (1.0f - beta) * s.c0 + beta * s.c;
+  float angle = (1.0f - beta) * s.a0 + beta * s.a;
+  xf.q = rot_set(angle);
+  xf.p = xf.p - rmul(xf.q, s.lc);
+  return xf;
+}
+__device__ __forceinline__ void sweep_normalize(SweepD& s) {
+  float twoPi = 2.0f * KB_PI;
+  float d = twoPi * floorf(s.a0 / twoPi);
+  s.a0 -= d;
+  s.a -= d;
+}
+
+// b2DistanceProxy over a scene proxy
+struct DProxy {
+  const ProxyConst* pc;
+  int type, count;
+  float radius;
+  __device__ __forceinline__ void set(const ProxyConst* p) {
+    pc = p;
+    type = __ldg(&p->type);
+    radius = __ldg(&p->radius);
+    count = type == SHAPE_CIRCLE ? 1 : (type == SHAPE_EDGE ? 2 : __ldg(&p->count));
+  }
+  __device__ __forceinline__ V2 vertex(int i) const {
+    if (type == SHAPE_CIRCLE) return mk(0.0f, 0.0f);
+    if (type == SHAPE_EDGE) return pvert(pc, 1 + i);
+    return pvert(pc, i);
+  }
+  __device__ __forceinline__ int support(V2 d) const {
+    int bestIndex = 0;
+    float bestValue = dot(vertex(0), d);
+    for (int i = 1; i < count; ++i) {
+      float value = dot(vertex(i), d);
+      if (value > bestValue) {
+        bestIndex = i;
+        bestValue = value;
+      }
+    }
+    return bestIndex;
+  }
+};
+
+struct SimplexCache {
+  float metric;
+  int count;
+  int indexA[3], indexB[3];
+};
+struct SimplexVertex {
+  V2 wA, wB, w;
+  float a;
+  int indexA, indexB;
+};
+
+struct Simplex {
+  SimplexVertex v[3];
+  int count;
+
+  __device__ float metric() const {
+    if (count == 2) return length(v[0].w - v[1].w);
+    if (count == 3) return cross(v[1].w - v[0].w, v[2].w - v[0].w);
+    return 0.0f;
+  }
+  __device__ void solve2() {
+    V2 w1 = v[0].w, w2 = v[1].w;
+    V2 e12 = w2 - w1;
+    float d12_2 = -dot(w1, e12);
+    if (d12_2 <= 0.0f) {
+      v[0].a = 1.0f;
+      count = 1;
+      return;
+    }
+    float d12_1 = dot(w2, e12);
+    if (d12_1 <= 0.0f) {
+      v[1].a = 1.0f;
+      count = 1;
+      v[0] = v[1];
+      return;
+    }
+    float inv_d12 = 1.0f / (d12_1 + d12_2);
+    v[0].a = d12_1 * inv_d12;
+    v[1].a = d12_2 * inv_d12;
+    count = 2;
+  }
+  __device__ void solve3() {
+    V2 w1 = v[0].w, w2 = v[1].w, w3 = v[2].w;
+    V2 e12 = w2 - w1;
+    float w1e12 = dot(w1, e12);
+    float w2e12 = dot(w2, e12);
+    float d12_1 = w2e12;
+    float d12_2 = -w1e12;
+    V2 e13 = w3 - w1;
+    float w1e13 = dot(w1, e13);
+    float w3e13 = dot(w3, e13);
+    float d13_1 = w3e13;
+    float d13_2 = -w1e13;
+    V2 e23 = w3 - w2;
+    float w2e23 = dot(w2, e23);
+    float w3e23 = dot(w3, e23);
+    float d23_1 = w3e23;
+    float d23_2 = -w2e23;
+    float n123 = cross(e12, e13);
+    float d123_1 = n123 * cross(w2, w3);
+    float d123_2 = n123 * cross(w3, w1);
+    float d123_3 = n123 * cross(w1, w2);
+    if (d12_2 <= 0.0f && d13_2 <= 0.0f) {
+      v[0].a = 1.0f;
+      count = 1;
+      return;
+    }
+    if (d12_1 > 0.0f && d12_2 > 0.0f && d123_3 <= 0.0f) {
+      float inv_d12 = 1.0f / (d12_1 + d12_2);
+      v[0].a = d12_1 * inv_d12;
+      v[1].a = d12_2 * inv_d12;
+      count = 2;
+      return;
+    }
+    if (d13_1 > 0.0f && d13_2 > 0.0f && d123_2 <= 0.0f) {
+      float inv_d13 = 1.0f / (d13_1 + d13_2);
+      v[0].a = d13_1 * inv_d13;
+      v[2].a = d13_2 * inv_d13;
+      count = 2;
+      v[1] = v[2];
+      return;
+    }
+    if (d12_1 <= 0.0f && d23_2 <= 0.0f) {
+      v[1].a = 1.0f;
+      count = 1;
+      v[0] = v[1];
+      return;
+    }
+    if (d13_1 <= 0.0f && d23_1 <= 0.0f) {
+      v[2].a = 1.0f;
+      count = 1;
+      v[0] = v[2];
+      return;
+    }
+    if (d23_1 > 0.0f && d23_2 > 0.0f && d123_1 <= 0.0f) {
+      float inv_d23 = 1.0f / (d23_1 + d23_2);
+      v[1].a = d23_1 * inv_d23;
+      v[2].a = d23_2 * inv_d23;
+      count = 2;
+      v[0] = v[2];
+      return;
+    }
+    float inv_d123 = 1.0f / (d123_1 + d123_2 + d123_3);
+    v[0].a = d123_1 * inv_d123;
+    v[1].a = d123_2 * inv_d123;
+    v[2].a = d123_3 * inv_d123;
+    count = 3;
+  }
+};
+
+// b2Distance(useRadii = false): distance between the core shapes; updates the cache.
+__device__ __noinline__ float gjk_distance(SimplexCache& cache, const DProxy& pA, Xf tA, const DProxy& pB, Xf tB) {
+  Simplex s;
+  s.count = cache.count;
+  for (int i = 0; i < s.count; ++i) {
+    SimplexVertex& sv = s.v[i];
+    sv.indexA = cache.indexA[i];
+    sv.indexB = cache.indexB[i];
+    sv.wA = xmul(tA, pA.vertex(sv.indexA));
+    sv.wB = xmul(tB, pB.vertex(sv.indexB));
+    sv.w = sv.wB - sv.wA;
+    sv.a = 0.0f;
+  }
+  if (s.count > 1) {
+    float metric1 = cache.metric;
+    float metric2 = s.metric();
+    if (metric2 < 0.5f * metric1 || 2.0f * metric1 < metric2 || metric2 < KB_EPS) s.count = 0;
+  }
+  if (s.count == 0) {
+    SimplexVertex& sv = s.v[0];
+    sv.indexA = 0;
+    sv.indexB = 0;
+    sv.wA = xmul(tA, pA.vertex(0));
+    sv.wB = xmul(tB, pB.vertex(0));
+    sv.w = sv.wB - sv.wA;
+    sv.a = 1.0f;
+    s.count = 1;
+  }
+  const int k_maxIters = 20;
+  int saveA[3], saveB[3];
+  int iter = 0;
+  while (iter < k_maxIters) {
+    int saveCount = s.count;
+    for (int i = 0; i < saveCount; ++i) {
+      saveA[i] = s.v[i].indexA;
+      saveB[i] = s.v[i].indexB;
+    }
+    if (s.count == 2) s.solve2();
+    else if (s.count == 3) s.solve3();
+    if (s.count == 3) break;
+    // search direction
+    V2 d;
+    if (s.count == 1) {
+      d = -s.v[0].w;
+    } else {
+      V2 e12 = s.v[1].w - s.v[0].w;
+      float sgn = cross(e12, -s.v[0].w);
+      d = sgn > 0.0f ? cross(1.0f, e12) : cross(e12, 1.0f);
+    }
+    if (dot(d, d) < KB_EPS * KB_EPS) break;
+    SimplexVertex& nv = s.v[s.count];
+    nv.indexA = pA.support(rmulT(tA.q, -d));
+    nv.wA = xmul(tA, pA.vertex(nv.indexA));
+    nv.indexB = pB.support(rmulT(tB.q, d));
+    nv.wB = xmul(tB, pB.vertex(nv.indexB));
+    nv.w = nv.wB - nv.wA;
+    ++iter;
+    bool duplicate = false;
+    for (int i = 0; i < saveCount; ++i) {
+      if (nv.indexA == saveA[i] && nv.indexB == saveB[i]) {
+        duplicate = true;
+        break;
+      }
+    }
+    if (duplicate) break;
+    ++s.count;
+  }
+  V2 pointA, pointB;
+  if (s.count == 1) {
+    pointA = s.v[0].wA;
+    pointB = s.v[0].wB;
+  } else if (s.count == 2) {
+    pointA = s.v[0].a * s.v[0].wA + s.v[1].a * s.v[1].wA;
+    pointB = s.v[0].a * s.v[0].wB + s.v[1].a * s.v[1].wB;
+  } else {
+    pointA = s.v[0].a * s.v[0].wA + s.v[1].a * s.v[1].wA + s.v[2].a * s.v[2].wA;
+    pointB = pointA;
+  }
+  float distance = length(pointA - pointB);
+  cache.metric = s.metric();
+  cache.count = s.count;
+  for (int i = 0; i < s.count; ++i) {
+    cache.indexA[i] = s.v[i].indexA;
+    cache.indexB[i] = s.v[i].indexB;
+  }
+  return distance;
+}
+
+// b2SeparationFunction
+struct SepFn {
+  const DProxy* pA;
+  const DProxy* pB;
+  SweepD sA, sB;
+  int type;  // 0 points, 1 faceA, 2 faceB
+  V2 localPoint, axis;
+
+  __device__ void initialize(const SimplexCache& cache, const DProxy* a, const SweepD& sa, const DProxy* b,
+                             const SweepD& sb, float t1) {
+    pA = a;
+    pB = b;
+    sA = sa;
+    sB = sb;
+    Xf xfA = sweep_xf(sA, t1), xfB = sweep_xf(sB, t1);
+    if (cache.count == 1) {
+      type = 0;
+      V2 pointA = xmul(xfA, pA->vertex(cache.indexA[0]));
+      V2 pointB = xmul(xfB, pB->vertex(cache.indexB[0]));
+      axis = pointB - pointA;
+      normalize(axis);
+    } else if (cache.indexA[0] == cache.indexA[1]) {
+      type = 2;
+      V2 localPointB1 = pB->vertex(cache.indexB[0]);
+      V2 localPointB2 = pB->vertex(cache.indexB[1]);
+      axis = cross(localPointB2 - localPointB1, 1.0f);
+      normalize(axis);
+      V2 normal = rmul(xfB.q, axis);
+      localPoint = 0.5f * (localPointB1 + localPointB2);
+      V2 pointB = xmul(xfB, localPoint);
+      V2 pointA = xmul(xfA, pA->vertex(cache.indexA[0]));
+      float s = dot(pointA - pointB, normal);
+      if (s < 0.0f) axis = -axis;
+    } else {
+      type = 1;
+      V2 localPointA1 = pA->vertex(cache.indexA[0]);
+      V2 localPointA2 = pA->vertex(cache.indexA[1]);
+      axis = cross(localPointA2 - localPointA1, 1.0f);
+      normalize(axis);
+      V2 normal = rmul(xfA.q, axis);
+      localPoint = 0.5f * (localPointA1 + localPointA2);
+      V2 pointA = xmul(xfA, localPoint);
+      V2 pointB = xmul(xfB, pB->vertex(cache.indexB[0]));
+      float s = dot(pointB - pointA, normal);
+      if (s < 0.0f) axis = -axis;
+    }
+  }
+  __device__ float findMinSeparation(int* indexA, int* indexB, float t) const {
+    Xf xfA = sweep_xf(sA, t), xfB = sweep_xf(sB, t);
+    if (type == 0) {
+      V2 axisA = rmulT(xfA.q, axis);
+      V2 axisB = rmulT(xfB.q, -axis);
+      *indexA = pA->support(axisA);
+      *indexB = pB->support(axisB);
+      V2 pointA = xmul(xfA, pA->vertex(*indexA));
+      V2 pointB = xmul(xfB, pB->vertex(*indexB));
+      return dot(pointB - pointA, axis);
+    } else if (type == 1) {
+      V2 normal = rmul(xfA.q, axis);
+      V2 pointA = xmul(xfA, localPoint);
+      V2 axisB = rmulT(xfB.q, -normal);
+      *indexA = -1;
+      *indexB = pB->support(axisB);
+      V2 pointB = xmul(xfB, pB->vertex(*indexB));
+      return dot(pointB - pointA, normal);
+    } else {
+      V2 normal = rmul(xfB.q, axis);
+      V2 pointB = xmul(xfB, localPoint);
+      V2 axisA = rmulT(xfA.q, -normal);
+      *indexB = -1;
+      *indexA = pA->support(axisA);
+      V2 pointA = xmul(xfA, pA->vertex(*indexA));
+      return dot(pointA - pointB, normal);
+    }
+  }
+  __device__ float evaluate(int indexA, int indexB, float t) const {
+    Xf xfA = sweep_xf(sA, t), xfB = sweep_xf(sB, t);
+    if (type == 0) {
+      V2 pointA = xmul(xfA, pA->vertex(indexA));
+      V2 pointB = xmul(xfB, pB->vertex(indexB));
+      return dot(pointB - pointA, axis);
+    } else if (type == 1) {
+      V2 normal = rmul(xfA.q, axis);
+      V2 pointA = xmul(xfA, localPoint);
+      V2 pointB = xmul(xfB, pB->vertex(indexB));
+      return dot(pointB - pointA, normal);
+    } else {
+      V2 normal = rmul(xfB.q, axis);
+      V2 pointB = xmul(xfB, localPoint);
+      V2 pointA = xmul(xfA, pA->vertex(indexA));
+      return dot(pointA - pointB, normal);
+    }
+  }
+};
+
+// b2TimeOfImpact with tMax = 1.  Returns true and *t if the state is e_touching.
+__device__ __noinline__ bool time_of_impact(const ProxyConst* shapeA, SweepD sweepA, const ProxyConst* shapeB,
+                                            SweepD sweepB, float* tOut) {
+  DProxy proxyA, proxyB;
+  proxyA.set(shapeA);
+  proxyB.set(shapeB);
+  sweep_normalize(sweepA);
+  sweep_normalize(sweepB);
+  const float tMax = 1.0f;
+  float totalRadius = proxyA.radius + proxyB.radius;
+  float target = b2max(KB_LINEAR_SLOP, totalRadius - 3.0f * KB_LINEAR_SLOP);
+  float tolerance = 0.25f * KB_LINEAR_SLOP;
+  float t1 = 0.0f;
+  const int k_maxIterations = 20;
+  int iter = 0;
+  SimplexCache cache;
+  cache.metric = 0.0f;
+  cache.count = 0;
+  for (;;) {
+    Xf xfA = sweep_xf(sweepA, t1), xfB = sweep_xf(sweepB, t1);
+    float distance = gjk_distance(cache, proxyA, xfA, proxyB, xfB);
+    if (distance <= 0.0f) return false;  // e_overlapped
+    if (distance < target + tolerance) {
+      *tOut = t1;
+      return true;  // e_touching
+    }
+    SepFn fcn;
+    fcn.initialize(cache, &proxyA, sweepA, &proxyB, sweepB, t1);
+    bool done = false;
+    float t2 = tMax;
+    int pushBackIter = 0;
+    for (;;) {
+      int indexA, indexB;
+      float s2 = fcn.findMinSeparation(&indexA, &indexB, t2);
+      if (s2 > target + tolerance) return false;  // e_separated
+      if (s2 > target - tolerance) {
+        t1 = t2;
+        break;
+      }
+      float s1 = fcn.evaluate(indexA, indexB, t1);
+      if (s1 < target - tolerance) return false;  // e_failed
+      if (s1 <= target + tolerance) {
+        *tOut = t1;
+        return true;  // e_touching
+      }
+      int rootIterCount = 0;
+      float a1 = t1, a2 = t2;
+      for (;;) {
+        float t;
+        if (rootIterCount & 1) t = a1 + (target - s1) * (a2 - a1) / (s2 - s1);
+        else t = 0.5f * (a1 + a2);
+        ++rootIterCount;
+        float s = fcn.evaluate(indexA, indexB, t);
+        if (b2abs(s - target) < tolerance) {
+          t2 = t;
+          break;
+        }
+        if (s > target) {
+          a1 = t;
+          s1 = s;
+        } else {
+          a2 = t;
+          s2 = s;
+        }
+        if (rootIterCount == 50) break;
+      }
+      ++pushBackIter;
+      if (pushBackIter == KB_MAX_POLY_VERTS) break;
+    }
+    ++iter;
+    if (done) break;
+    if (iter == k_maxIterations) return false;  // e_failed
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------ b2World::SolveTOI
+template <int LPE>
+__device__ void Sim<LPE>::solveTOI() {
+  const int B = L.B;
+  float* toi = reinterpret_cast<float*>(sm + L.sToi);  // cached alpha per contact
+  int nC = (int)hdr(H_NC);
+  // any contact with the table at all?  (the common case is none: skip everything)
+  bool wallContact = false;
+  for (int i = g.lane; i < nC; i += LPE) wallContact |= __ldg(&px[cpair(i) & 0xFFFF].body) == S;
+  if (!g.any(wallContact)) return;
+
+  for (int b = g.lane; b <= B; b += LPE) reinterpret_cast<float*>(&sweep4(b))[3] = 0.0f;  // alpha0 = 0
+  for (int i = g.lane; i < nC; i += LPE) {
+    cinfo(i) &= ~(CI_TOI | CI_ISLAND | CI_TOICOUNT_MASK);
+    toi[i] = 1.0f;
+  }
+  g.sync();
+
+  for (int guard = 0; guard < 64 * KB_MAX_SUB_STEPS; ++guard) {
+    nC = (int)hdr(H_NC);
+    const float tableAlpha0 = sweep4(S).w;
+    // ---- per-contact TOI (lane parallel).  Bodies lagging behind the table's alpha0 are
+    //      advanced first (b2Sweep::Advance is idempotent for a common target).
+    for (int base = 0; base < nC; base += LPE) {
+      const int i = base + g.lane;
+      bool need = false;
+      int pa = 0, pb = 0, bd = S;
+      if (i < nC) {
+        const uint32_t info = cinfo(i);
+        const bool enabled = (info & CI_ENABLED) != 0u;
+        const int toiCount = (info & CI_TOICOUNT_MASK) >> CI_TOICOUNT_SHIFT;
+        if (enabled && toiCount <= KB_MAX_SUB_STEPS && (info & CI_TOI) == 0u) {
+          const uint32_t pr = cpair(i);
+          pa = pr & 0xFFFF;
+          pb = pr >> 16;
+          const int bA = __ldg(&px[pa].body), bB = __ldg(&px[pb].body);
+          // chain is always fixture A, so the table can only be body A
+          if (bA == S && bB != S && awake(bB)) {
+            need = true;
+            bd = bB;
+          }
+        }
+      }
+      if (need) {
+        float4 sw = sweep4(bd);
+        if (sw.w < tableAlpha0) {
+          // b2Sweep::Advance(alpha0)
+          const float4 p = pos4(bd);
+          float beta = (tableAlpha0 - sw.w) / (1.0f - sw.w);
+          sw.x += beta * (p.x - sw.x);
+          sw.y += beta * (p.y - sw.y);
+          sw.z += beta * (p.z - sw.z);
+          sw.w = tableAlpha0;
+          sweep4(bd) = sw;
+        }
+      }
+      g.sync();
+      if (need) {
+        const float4 sw = sweep4(bd);
+        const float4 p = pos4(bd);
+        const float4 k = bc4(bd);
+        SweepD sA, sB;
+        sA.lc = mk(0.0f, 0.0f); sA.c0 = mk(0.0f, 0.0f); sA.c = mk(0.0f, 0.0f);
+        sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = tableAlpha0;
+        sB.lc = mk(k.z, k.w); sB.c0 = mk(sw.x, sw.y); sB.c = mk(p.x, p.y);
+        sB.a0 = sw.z; sB.a = p.z; sB.alpha0 = sw.w;
+        const float alpha0 = tableAlpha0;
+        float beta = 1.0f;
+        float alpha = 1.0f;
+        if (time_of_impact(px + pa, sA, px + pb, sB, &beta)) alpha = b2min(alpha0 + (1.0f - alpha0) * beta, 1.0f);
+        toi[i] = alpha;
+        cinfo(i) |= CI_TOI;
+      }
+      g.sync();
+    }
+    // ---- minimum alpha, first in world-list order (highest index) on ties
+    uint32_t bestBits = f2u(1.0f);
+    int bestIdx = -1;
+    for (int base = 0; base < nC; base += LPE) {
+      const int i = base + g.lane;
+      if (i < nC) {
+        const uint32_t info = cinfo(i);
+        const int toiCount = (info & CI_TOICOUNT_MASK) >> CI_TOICOUNT_SHIFT;
+        if ((info & CI_ENABLED) != 0u && toiCount <= KB_MAX_SUB_STEPS && (info & CI_TOI) != 0u) {
+          const float alpha = toi[i];
+          if (alpha < 1.0f) {
+            const uint32_t bits = f2u(alpha);
+            if (bits < bestBits || (bits == bestBits && i > bestIdx)) {
+              bestBits = bits;
+              bestIdx = i;
+            }
+          }
+        }
+      }
+    }
+    const uint32_t minBits = __reduce_min_sync(g.gmask, bestBits);
+    const int cand = (bestBits == minBits && bestIdx >= 0) ? bestIdx : -1;
+    const int minContact = (int)__reduce_max_sync(g.gmask, (uint32_t)(cand + 1)) - 1;
+    const float minAlpha = u2f(minBits);
+    if (minContact < 0 || 1.0f - 10.0f * KB_EPS < minAlpha) break;
+
+    if (g.lane == 0) counters()[KB_CNT_TOI_EVENTS] += 1ull;
+    const uint32_t mpr = cpair(minContact);
+    const int bd = __ldg(&px[mpr >> 16].body);  // the dynamic body (fixture B)
+    // backups, advance both bodies to minAlpha (b2Body::Advance)
+    const float4 backupSweep = sweep4(bd), backupPos = pos4(bd), backupXf = xf4(bd);
+    const float4 backupTable = sweep4(S);
+    g.sync();
+    if (g.lane == 0) {
+      float4 sw = sweep4(bd);
+      float4 p = pos4(bd);
+      const float4 k = bc4(bd);
+      float beta = (minAlpha - sw.w) / (1.0f - sw.w);
+      sw.x += beta * (p.x - sw.x);
+      sw.y += beta * (p.y - sw.y);
+      sw.z += beta * (p.z - sw.z);
+      sw.w = minAlpha;
+      p.x = sw.x; p.y = sw.y; p.z = sw.z;
+      sweep4(bd) = sw;
+      pos4(bd) = p;
+      Rot q = rot_set(p.z);
+      V2 o = mk(p.x, p.y) - rmul(q, mk(k.z, k.w));
+      xf4(bd) = make_float4(o.x, o.y, q.s, q.c);
+      reinterpret_cast<float*>(&sweep4(S))[3] = minAlpha;
+      // minContact->Update()
+      updateContact(minContact);
+      uint32_t info = cinfo(minContact);
+      info &= ~CI_TOI;
+      const uint32_t tc = ((info & CI_TOICOUNT_MASK) >> CI_TOICOUNT_SHIFT) + 1u;
+      info = (info & ~CI_TOICOUNT_MASK) | (tc << CI_TOICOUNT_SHIFT);
+      cinfo(minContact) = info;
+    }
+    g.sync();
+    if ((cinfo(minContact) & CI_TOUCHING) == 0u) {
+      if (g.lane == 0) {
+        cinfo(minContact) &= ~CI_ENABLED;
+        sweep4(bd) = backupSweep;
+        // restoring m_sweep leaves c/a at the backup values; SynchronizeTransform
+        pos4(bd) = backupPos;
+        xf4(bd) = backupXf;
+        sweep4(S) = backupTable;
+      }
+      g.sync();
+      continue;
+    }
+    if (g.lane == 0) wake(bd);
+    g.sync();
+    // ---- mini island: minContact first, then the body's other touching wall contacts in list order
+    //      (each re-evaluated at the advanced pose)
+    int nIsland = 1;
+    if (g.lane == 0) ordC(0) = (uint32_t)minContact;
+    for (int base = 0; base < nC; base += LPE) {
+      const int i = nC - 1 - (base + g.lane);
+      bool add = false;
+      if (i >= 0 && i != minContact) {
+        const uint32_t pr = cpair(i);
+        const int bA = __ldg(&px[pr & 0xFFFF].body), bB = __ldg(&px[pr >> 16].body);
+        if (bA == S && bB == bd) {
+          updateContact(i);
+          add = (cinfo(i) & (CI_ENABLED | CI_TOUCHING)) == (CI_ENABLED | CI_TOUCHING);
+        }
+      }
+      const uint32_t m = g.ballot(add);
+      const int dst = nIsland + __popc(m & g.lt());
+      if (add && dst < KB_MAX_TOI_CONTACTS && 3 * dst + 3 <= L.Kmax) ordC(dst) = (uint32_t)i;
+      nIsland = min(nIsland + __popc(m), min(KB_MAX_TOI_CONTACTS, L.Kmax / 3));
+    }
+    g.sync();
+    // ---- b2Island::SolveTOI (one dynamic body: strictly sequential, lane 0)
+    if (g.lane == 0) {
+      const float subDt = (1.0f - minAlpha) * L.dt;
+      for (int k = 0; k < nIsland; ++k) {
+        const int ci = ordC(k) & 0xFFFF;
+        const uint32_t pr = cpair(ci);
+        const int pc = (cinfo(ci) & CI_PC_MASK) >> CI_PC_SHIFT;
+        ordB(k) = (uint32_t)S | ((uint32_t)bd << 8) | (3u << 16) | ((uint32_t)pc << 24);
+        (void)pr;
+        entry(k) = (uint32_t)k | ((uint32_t)(3 * k) << 16);
+      }
+      // position constraints first: load manifold data into the pool (position layout)
+      for (int k = 0; k < nIsland; ++k) {
+        const int q = 3 * k;
+        const int ci = ordC(k) & 0xFFFF;
+        const float4* rec = reinterpret_cast<const float4*>(manifoldRec(ci));
+        const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+        const uint32_t tp = f2u(r3.z);
+        const int type = tp & 0xFF, pointCount = (tp >> 8) & 0xFF;
+        const uint32_t pr = cpair(ci);
+        poolu(PF_IDX, q) = (uint32_t)S | ((uint32_t)bd << 8) | ((uint32_t)pointCount << 16) | (1u << 20) |
+                           ((uint32_t)type << 24) | ((uint32_t)pointCount << 28);
+        poolu(PF_AUX, q) = (uint32_t)ci;
+        pool(PF_NX, q) = r0.x;
+        pool(PF_NY, q) = r0.y;
+        pool(PF_RAX, q) = r0.z;
+        pool(PF_RAY, q) = r0.w;
+        pool(PF_RBX, q) = __ldg(&px[pr & 0xFFFF].radius);
+        pool(PF_RBY, q) = __ldg(&px[pr >> 16].radius);
+        gw(q, 10) = r1.x;
+        gw(q, 11) = r1.y;
+        gw(q, 12) = r2.y;
+        gw(q, 13) = r2.z;
+      }
+      for (int it = 0; it < 20; ++it) {
+        bool ok = true;
+        for (int k = 0; k < nIsland; ++k) ok &= solvePositionOne(3 * k, KB_TOI_BAUMGARTE, -1.5f * KB_LINEAR_SLOP, S, bd);
+        if (ok) break;
+      }
+      {
+        const float4 p = pos4(bd);
+        float* sw = reinterpret_cast<float*>(&sweep4(bd));
+        sw[0] = p.x; sw[1] = p.y; sw[2] = p.z;  // c0, a0 = corrected pose
+      }
+      // velocity constraints without warm starting, at the corrected pose
+      for (int k = 0; k < nIsland; ++k) initConstraint(k, true);
+      for (int it = 0; it < L.velIters; ++it)
+        for (int k = 0; k < nIsland; ++k) solveVelocityOne(3 * k);
+      // integrate the remainder of the step
+      {
+        const float h = subDt;
+        float4 p = pos4(bd);
+        float4 v = vel4(bd);
+        const float4 kk = bc4(bd);
+        V2 translation = h * mk(v.x, v.y);
+        if (dot(translation, translation) > KB_MAX_TRANSLATION_SQ) {
+          float ratio = KB_MAX_TRANSLATION / length(translation);
+          v.x *= ratio;
+          v.y *= ratio;
+        }
+        float rotation = h * v.z;
+        if (rotation * rotation > KB_MAX_ROTATION_SQ) {
+          float ratio = KB_MAX_ROTATION / b2abs(rotation);
+          v.z *= ratio;
+        }
+        p.x += h * v.x;
+        p.y += h * v.y;
+        p.z += h * v.z;
+        pos4(bd) = p;
+        vel4(bd) = v;
+        Rot q = rot_set(p.z);
+        V2 o = mk(p.x, p.y) - rmul(q, mk(kk.z, kk.w));
+        xf4(bd) = make_float4(o.x, o.y, q.s, q.c);
+      }
+      for (int b = 0; b <= B; ++b) isl(b) = b == bd ? 0 : -1;
+    }
+    g.sync();
+    synchronizeFixtures(true);
+    // invalidate the cached TOIs of every contact of the displaced body
+    for (int i = g.lane; i < nC; i += LPE) {
+      const uint32_t pr = cpair(i);
+      if (__ldg(&px[pr & 0xFFFF].body) == bd || __ldg(&px[pr >> 16].body) == bd) cinfo(i) &= ~(CI_TOI | CI_ISLAND);
+    }
+    g.sync();
+    const int before = (int)hdr(H_NC);
+    findNewContacts();
+    const int after = (int)hdr(H_NC);
+    for (int i = before + g.lane; i < after; i += LPE) toi[i] = 1.0f;
+    g.sync();
+  }
+}
+
+}  // namespace kb

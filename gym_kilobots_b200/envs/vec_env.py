@@ -1,0 +1,109 @@
+"""KilobotsVecEnv -- the vectorised N-env wrapper around the batched CUDA step.
+
+The reference steps one environment per Python call (gym_kilobots/envs/kilobots_env.py:161-215);
+this class steps E of them with one kernel launch.  Semantics per environment are exactly those of
+`KilobotsEnv.step` / `reset`; the observation keeps the reference's dict layout
+({'kilobots': [N,3], 'objects': [M,3], 'light': [L]}, kilobots_env.py:115-118) with a leading env axis.
+"""
+import numpy as np
+
+from .. import _abi as abi
+from .. import _native
+
+
+class KilobotsVecEnv:
+    """E independent Kilobots environments on one GPU.
+
+    scenario: a `gym_kilobots_b200.scenarios.Scenario` (scene templates + initial poses), or anything
+    with the attributes scenes / env_scene / body_pose / light_state / max_contacts.
+    """
+
+    def __init__(self, scenario, device=0, action_mode=abi.KB_ACTION_LIGHT):
+        self.scenario = scenario
+        self.batch = _native.NativeBatch(scenario.scenes, scenario.body_pose.shape[0], scenario.env_scene,
+                                         scenario.max_contacts, device=device)
+        self.num_envs = self.batch.E
+        self.num_kilobots = self.batch.N
+        self.num_objects = self.batch.M
+        self.action_mode = action_mode
+        self.action_dim = 2 * self.batch.N if action_mode == abi.KB_ACTION_KILOBOTS else self.batch.A
+        self._host = None
+        self._sim_steps = 0
+
+    # -- gym-like surface ---------------------------------------------------------------------
+    @property
+    def action_space(self):
+        from ..spaces import Box
+        sc = self.scenario.scenes[0]
+        lo = np.concatenate([np.asarray(l.action_bounds[0], float).ravel()[:l.action_dim] for l in sc.lights]) \
+            if sc.lights else np.zeros(0)
+        hi = np.concatenate([np.asarray(l.action_bounds[1], float).ravel()[:l.action_dim] for l in sc.lights]) \
+            if sc.lights else np.zeros(0)
+        return Box(lo, hi, dtype=np.float64)
+
+    def reset(self, body_pose=None, light_state=None, kb_velocity=None, mask=None):
+        """KilobotsEnv.reset for every (masked) env: rebuild bodies at the poses, one settle step."""
+        pose = self.scenario.body_pose if body_pose is None else body_pose
+        light = self.scenario.light_state if light_state is None else light_state
+        self.batch.reset(pose, light, kb_velocity, mask)
+        self._sim_steps = 0
+        return self.get_observation()
+
+    def step_device(self, action):
+        """Device tensors in, device tensors out, no synchronisation (training-loop path)."""
+        k, o, l, r, d, s = self.batch.step_device(action, self.action_mode if action is not None else None)
+        self._sim_steps += self.scenario.scenes[0].steps_per_action
+        return {"kilobots": k, "objects": o, "light": l}, r, d, {"status": s}
+
+    def _host_buffers(self):
+        if self._host is None:
+            import torch
+            b = self.batch
+            pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
+            self._host = {
+                "action": pin((b.E, max(self.action_dim, 1)), torch.float64),
+                "kilobots": pin((b.E, b.N, 3), torch.float32),
+                "objects": pin((b.E, b.M, 3), torch.float32),
+                "light": pin((b.E, b.L), torch.float64),
+                "reward": pin((b.E,), torch.float32),
+                "done": pin((b.E,), torch.uint8),
+                "status": pin((b.E,), torch.int32),
+            }
+        return self._host
+
+    def step(self, action):
+        """Host numpy in, host numpy out (pinned staging, copies inside the call): the drop-in path.
+
+        Returns (observation dict, reward [E], done [E], info) like KilobotsEnv.step."""
+        hb = self._host_buffers()
+        if action is None:
+            mode, act = abi.KB_ACTION_NONE, None
+        else:
+            mode = self.action_mode
+            act = hb["action"]
+            act[...] = np.asarray(action, dtype=np.float64).reshape(act.shape)
+        self.batch.step_host(act, mode, hb)
+        self._sim_steps += self.scenario.scenes[0].steps_per_action
+        obs = {"kilobots": hb["kilobots"], "objects": hb["objects"], "light": hb["light"]}
+        return obs, hb["reward"], hb["done"].astype(bool), {"status": hb["status"]}
+
+    def host_io_bytes(self):
+        """(bytes host->device, bytes device->host) moved by one `step` call."""
+        hb = self._host_buffers()
+        h2d = hb["action"].nbytes if self.action_dim > 0 else 0
+        d2h = sum(hb[k].nbytes for k in ("kilobots", "objects", "light", "reward", "done", "status"))
+        return h2d, d2h
+
+    def get_state(self):
+        b = self.batch.bodies()
+        _, light = self.batch.controllers()
+        M = self.num_objects
+        pose = np.stack([b[..., 8].astype(np.float64) / 25.0, b[..., 9].astype(np.float64) / 25.0,
+                         b[..., 2].astype(np.float64)], axis=-1)
+        return {"kilobots": pose[:, M:], "objects": pose[:, :M], "light": light}
+
+    def get_observation(self):
+        return self.get_state()
+
+    def close(self):
+        self.batch.close()

@@ -1,0 +1,149 @@
+"""Synthetic scene batches for the BASELINE.json configurations.
+
+Each builder returns a `Scenario`: scene template(s), the env->scene map and seeded float64 initial
+poses / light states for E environments.  Sampling mirrors the reference's scene builders
+(gym_kilobots/envs/yaml_kilobots_env.py:194-198,256-265,327-354 and
+envs/kilobots_test_envs.py:23-82) but is vectorised over E and uses a seeded numpy Generator keyed
+by the global env id, so a slice of a batch (one rank of N) sees the same per-env draws.
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from . import _abi as abi
+from . import scene as S
+
+
+@dataclass
+class Scenario:
+    name: str
+    scenes: List[S.SceneSpec]
+    env_scene: Optional[np.ndarray]
+    body_pose: np.ndarray          # [E, B, 3] float64 (m, m, rad)
+    light_state: np.ndarray        # [E, L] float64
+    max_contacts: int = 0
+
+    @property
+    def num_envs(self):
+        return self.body_pose.shape[0]
+
+
+def _rng_for(seed, env_ids):
+    """Independent per-env streams: results do not depend on how envs are split across ranks."""
+    return [np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, 0, int(i)])) for i in env_ids]
+
+
+def _separated_gaussian(rngs, mean, std, n, lo, hi, min_dist, max_tries=200):
+    """[E, n, 2] positions ~ N(mean, std^2), clipped to [lo, hi], pairwise >= min_dist (rejection)."""
+    E = len(rngs)
+    out = np.zeros((E, n, 2))
+    for e, rng in enumerate(rngs):
+        pts = []
+        for k in range(n):
+            for _ in range(max_tries):
+                p = rng.normal(scale=std, size=2) + mean[e]
+                p = np.minimum(np.maximum(p, lo), hi)
+                if all(np.hypot(*(p - q)) >= min_dist for q in pts):
+                    break
+            pts.append(p)
+        out[e] = np.asarray(pts)
+    return out
+
+
+def _circular_light(radius, world_size):
+    w, h = world_size
+    bounds = (np.array([-w / 2, -h / 2]) * 1.1, np.array([w / 2, h / 2]) * 1.1)   # yaml_kilobots_env.py:270
+    return S.LightSpec(abi.KB_LIGHT_CIRCULAR, radius=radius, bounds=bounds,
+                       action_bounds=(np.array([-1, -1]) * .01, np.array([1, 1]) * .01))  # :280
+
+
+def c1_single_env(num_envs=1, seed=0, env_offset=0, kilobot_kind=abi.KB_KILOBOT_PHOTOTAXIS, **scene_kw):
+    """C1: 10 phototaxis kilobots + 1 square object + circular gradient light (YamlKilobotsEnv-style)."""
+    world = (2.0, 1.5)
+    sc = S.SceneSpec(bodies=[S.quad_body(.15, .15)] + [S.kilobot_body(kilobot_kind) for _ in range(10)],
+                     num_objects=1, lights=[_circular_light(.2, world)], world_size=world, **scene_kw)
+    rngs = _rng_for(seed, range(env_offset, env_offset + num_envs))
+    wb = np.array([world[0] / 2, world[1] / 2])
+    light = np.stack([(r.random(2) * 2 * wb - wb) * 0.9 for r in rngs])
+    kb = _separated_gaussian(rngs, light, 0.03, 10, -wb + 0.02, wb - 0.02, 2 * S.KILOBOT_RADIUS + 1e-3)
+    pose = np.zeros((num_envs, 11, 3))
+    pose[:, 1:, :2] = kb
+    return Scenario("C1", [sc], None, pose, light, max_contacts=128)
+
+
+def c2_quad_assembly(num_envs=4096, seed=0, env_offset=0, degenerate=True, **scene_kw):
+    """C2: QuadAssemblyKilobotsEnv (kilobots_test_envs.py:23-82): 15 PhototaxisKilobots + 4 CornerQuads.
+
+    degenerate=True reproduces the reference spawn (3 coincident copies of a 5-point cross);
+    degenerate=False is C2' (same scene, kilobots ~ N(S, 0.03^2) rejection-separated)."""
+    world = (2.0, 1.5)
+    sc = S.SceneSpec(bodies=[S.quad_body(.15, .15) for _ in range(4)] +
+                     [S.kilobot_body(abi.KB_KILOBOT_PHOTOTAXIS) for _ in range(15)],
+                     num_objects=4, lights=[S.LightSpec(abi.KB_LIGHT_CIRCULAR, radius=.2)], world_size=world,
+                     reward_const=1.0, **scene_kw)
+    rngs = _rng_for(seed, range(env_offset, env_offset + num_envs))
+    swarm = np.stack([np.array([-.95, -.7]) + r.random(2) * np.array([.9, 1.4]) for r in rngs])
+    obj = np.stack([np.array([.05, -.7]) + r.random(2) * np.array([.9, .65]) for r in rngs])
+    pose = np.zeros((num_envs, 19, 3))
+    pose[:, 0] = (.45, .605, 0.0)
+    pose[:, 1] = (.605, .605, -np.pi / 2)
+    pose[:, 2] = (.605, .45, -np.pi)
+    pose[:, 3, :2] = obj
+    pose[:, 3, 2] = -np.pi / 2
+    if degenerate:
+        offs = np.array([(.0, .0), (.03, .0), (.0, .03), (-.03, .0), (.0, -.03)] * 3)
+        pose[:, 4:, :2] = swarm[:, None, :] + offs[None]
+    else:
+        wb = np.array([world[0] / 2, world[1] / 2])
+        pose[:, 4:, :2] = _separated_gaussian(rngs, swarm, 0.03, 15, -wb + 0.02, wb - 0.02,
+                                              2 * S.KILOBOT_RADIUS + 1e-3)
+    return Scenario("C2" if degenerate else "C2'", [sc], None, pose, swarm.copy(), max_contacts=160)
+
+
+def c3_shapes(num_envs=8192, seed=0, env_offset=0, num_kilobots=50, **scene_kw):
+    """C3: 50 kilobots + 1 object of shape [LForm, Triangle, Circle][env_id % 3]."""
+    world = (2.0, 1.5)
+    kb = [S.kilobot_body(abi.KB_KILOBOT_PHOTOTAXIS) for _ in range(num_kilobots)]
+    objs = [S.polygon_body(S.LFORM_TEMPLATE, .15, .15), S.polygon_body(S.TRIANGLE_TEMPLATE, .15, .15), S.circle_body(.075)]
+    scenes = [S.SceneSpec(bodies=[o] + kb, num_objects=1, lights=[_circular_light(.2, world)], world_size=world,
+                          **scene_kw) for o in objs]
+    ids = np.arange(env_offset, env_offset + num_envs)
+    rngs = _rng_for(seed, ids)
+    wb = np.array([world[0] / 2, world[1] / 2])
+    light = np.stack([(r.random(2) * 2 * wb - wb) * 0.9 for r in rngs])
+    pose = np.zeros((num_envs, 1 + num_kilobots, 3))
+    for e, r in enumerate(rngs):
+        pose[e, 0, :2] = (r.random(2) * 2 * wb - wb) * 0.7           # yaml_kilobots_env.py:194-198
+        pose[e, 0, 2] = r.random() * 2 * np.pi - np.pi
+    pose[:, 1:, :2] = _separated_gaussian(rngs, light, 0.06, num_kilobots, -wb + 0.02, wb - 0.02,
+                                          2 * S.KILOBOT_RADIUS + 1e-3)
+    for e, r in enumerate(rngs):
+        pose[e, 1:, 2] = r.random(num_kilobots) * 2 * np.pi - np.pi
+    return Scenario("C3", scenes, (ids % 3).astype(np.int32), pose, light, max_contacts=320)
+
+
+def c5_small(num_envs=1 << 20, seed=0, env_offset=0, **scene_kw):
+    """C5: 4 kilobots + 1 Quad(0.15, 0.15); throughput sweep.  Vectorised sampling (E is large)."""
+    world = (2.0, 1.5)
+    sc = S.SceneSpec(bodies=[S.quad_body(.15, .15)] + [S.kilobot_body(abi.KB_KILOBOT_PHOTOTAXIS) for _ in range(4)],
+                     num_objects=1, lights=[_circular_light(.2, world)], world_size=world, **scene_kw)
+    rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, 1, int(env_offset)]))
+    wb = np.array([world[0] / 2, world[1] / 2])
+    light = (rng.random((num_envs, 2)) * 2 * wb - wb) * 0.9
+    # kilobots on a jittered 2x2 block around the light: separated by construction
+    base = np.array([(-.02, -.02), (.02, -.02), (-.02, .02), (.02, .02)])
+    jit = rng.uniform(-.002, .002, size=(num_envs, 4, 2))
+    pose = np.zeros((num_envs, 5, 3))
+    pose[:, 0, :2] = (rng.random((num_envs, 2)) * 2 * wb - wb) * 0.7
+    pose[:, 0, 2] = rng.random(num_envs) * 2 * np.pi - np.pi
+    pose[:, 1:, :2] = np.minimum(np.maximum(light[:, None, :] + base[None] + jit, -wb + 0.02), wb - 0.02)
+    pose[:, 1:, 2] = rng.random((num_envs, 4)) * 2 * np.pi - np.pi
+    return Scenario("C5", [sc], None, pose, light, max_contacts=32)
+
+
+def random_actions(scenario_or_dim, num_envs, steps, seed=1):
+    """i.i.d. U([-0.01, 0.01]^A) per env-step: mirrors env.action_space.sample() (gym_kilobots/test.py:25)."""
+    A = scenario_or_dim if isinstance(scenario_or_dim, int) else scenario_or_dim.scenes[0].action_dim
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    return rng.uniform(-0.01, 0.01, size=(steps, num_envs, A))
