@@ -164,3 +164,56 @@ def sincosf(a, libm=False):
     c = np.empty_like(a)
     (lib.kbo_libm_sincosf if libm else lib.kbo_sincosf)(_ptr(a), _ptr(s), _ptr(c), a.size)
     return s, c
+
+
+# ---- golden-vector hooks (single pieces of the Python-side restatement) ---------------------------
+def _light_defs(specs):
+    from gym_kilobots_b200.scene import SceneSpec
+    d, keep = SceneSpec(lights=list(specs)).to_desc()
+    return d.lights, keep
+
+
+def eval_light(specs, state, pts):
+    lib, _ = load()
+    defs, keep = _light_defs(specs)
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    state = np.ascontiguousarray(state, dtype=np.float64)
+    value = np.zeros(len(pts))
+    grad = np.zeros((len(pts), 2))
+    lib.kbo_eval_light.restype = None
+    lib.kbo_eval_light.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.kbo_eval_light(C.cast(defs, C.c_void_p), len(specs), _ptr(state), _ptr(pts), len(pts), _ptr(value), _ptr(grad))
+    return value, grad
+
+
+def light_step(spec, state, action, substeps):
+    lib, _ = load()
+    defs, keep = _light_defs([spec])
+    state = np.ascontiguousarray(state, dtype=np.float64).copy()
+    action = np.ascontiguousarray(action, dtype=np.float64)
+    trace = np.zeros((substeps, len(state)))
+    lib.kbo_light_step.restype = None
+    lib.kbo_light_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.kbo_light_step(C.cast(defs, C.c_void_p), _ptr(state), _ptr(action), substeps, _ptr(trace))
+    return state, trace
+
+
+def controller_trace(kind, pose_b2, feed, velocity=None):
+    lib, _ = load()
+    feed = np.ascontiguousarray(feed, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((len(feed), 3), np.float32)
+    vel = None if velocity is None else np.ascontiguousarray(velocity, dtype=np.float64)
+    lib.kbo_controller_trace.restype = None
+    lib.kbo_controller_trace.argtypes = [C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_void_p]
+    lib.kbo_controller_trace(kind, pose_b2[0], pose_b2[1], pose_b2[2], _ptr(vel), _ptr(feed), len(feed), _ptr(out))
+    return out
+
+
+def sensor_pos(x, y, angle):
+    lib, _ = load()
+    out = np.zeros(2)
+    lib.kbo_sensor_pos.restype = None
+    lib.kbo_sensor_pos.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p]
+    lib.kbo_sensor_pos(x, y, angle, _ptr(out))
+    return out

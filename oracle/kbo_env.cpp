@@ -251,6 +251,69 @@ static void LightValueGrad(const KbLightDef& ld, const LightState& ls, double px
   *gy = g1;
 }
 
+// Kilobot.step for one kilobot (kilobots_env.py:183-184 -> lib/kilobot.py)
+static void RunController(const Handle* h, KilobotCtrl& kc, Body* b, float dtf, double dt) {
+  switch (kc.kind) {
+    case KB_KILOBOT_PHOTOTAXIS: {
+      // _loop lib/kilobot.py:318-333
+      if (kc.updateCounter % 6) {
+        kc.updateCounter += 1;
+      } else {
+        kc.updateCounter += 1;
+        double m = kc.lightValue;  // get_ambientlight :57-61 (falsy -> 0)
+        if (m > kc.threshold || kc.noChangeCounter >= 15) {
+          kc.threshold = m + .01;
+          kc.turnRight = kc.turnRight ? 0 : 1;  // switch_directions :67-71
+          kc.noChangeCounter = 0;
+        } else {
+          kc.noChangeCounter += 1;
+        }
+      }
+      // Kilobot.step single-motor branches :103-127
+      const float* t = kc.turnRight ? h->transRight : h->transLeft;
+      float w_ = kc.turnRight ? h->omegaRight : h->omegaLeft;
+      Vec2 wv = b->GetWorldVector(Vec2(t[0], t[1]));
+      // b2Vec2 / _world_scale / time_step, then * _world_scale: float32 ops in pybox2d
+      Vec2 lv(wv.x / 25.0f, wv.y / 25.0f);
+      lv.Set(lv.x / dtf, lv.y / dtf);
+      lv.Set(lv.x * 25.0f, lv.y * 25.0f);
+      b->SetAngularVelocity(w_);
+      b->SetLinearVelocity(lv);
+    } break;
+    case KB_KILOBOT_SIMPLE_PHOTOTAXIS: {  // :191-203
+      double mx = kc.lightGrad[0], my = kc.lightGrad[1];
+      double n = std::sqrt(mx * mx + my * my);
+      if (n > 0.01) {
+        mx = mx / n * 0.01;
+        my = my / n * 0.01;
+      }
+      mx *= 25.0;
+      my *= 25.0;
+      b->SetLinearVelocity(Vec2((float)mx, (float)my));
+      b->linearDamping = .0f;
+    } break;
+    case KB_KILOBOT_ACCELERATION:  // :294-300
+      kc.velocity[0] += kc.acceleration[0] * dt;
+      kc.velocity[1] += kc.acceleration[1] * dt;
+      kc.velocity[0] = kc.velocity[0] > .0 ? kc.velocity[0] : .0;
+      kc.velocity[1] = kc.velocity[1] > -0.5 * M_PI ? kc.velocity[1] : -0.5 * M_PI;
+      kc.velocity[0] = kc.velocity[0] < 0.01 ? kc.velocity[0] : 0.01;
+      kc.velocity[1] = kc.velocity[1] < 0.5 * M_PI ? kc.velocity[1] : 0.5 * M_PI;
+      // fallthrough
+    case KB_KILOBOT_VELOCITY: {  // :253-258
+      double ang = (double)b->sweep.a;
+      double lx, ly;  // np.cos/np.sin via the shared double sincos (kbo_math.h)
+      SinCosD(ang, &ly, &lx);
+      lx *= kc.velocity[0] * 25.0;
+      ly *= kc.velocity[0] * 25.0;
+      b->SetLinearVelocity(Vec2((float)lx, (float)ly));
+      b->SetAngularVelocity((float)kc.velocity[1]);
+    } break;
+    default: break;
+  }
+
+}
+
 static void StepEnv(Handle* h, Env* e, const double* action, int actionMode) {
   const Scene& sc = h->scenes[e->scene];
   World* w = e->world;
@@ -326,68 +389,7 @@ static void StepEnv(Handle* h, Env* e, const double* action, int actionMode) {
       }
     }
     // controllers, kilobots_env.py:183-184
-    for (int k = 0; k < N; ++k) {
-      Body* b = e->bodies[M + k];
-      KilobotCtrl& kc = e->ctrl[k];
-      switch (kc.kind) {
-        case KB_KILOBOT_PHOTOTAXIS: {
-          // _loop lib/kilobot.py:318-333
-          if (kc.updateCounter % 6) {
-            kc.updateCounter += 1;
-          } else {
-            kc.updateCounter += 1;
-            double m = kc.lightValue;  // get_ambientlight :57-61 (falsy -> 0)
-            if (m > kc.threshold || kc.noChangeCounter >= 15) {
-              kc.threshold = m + .01;
-              kc.turnRight = kc.turnRight ? 0 : 1;  // switch_directions :67-71
-              kc.noChangeCounter = 0;
-            } else {
-              kc.noChangeCounter += 1;
-            }
-          }
-          // Kilobot.step single-motor branches :103-127
-          const float* t = kc.turnRight ? h->transRight : h->transLeft;
-          float w_ = kc.turnRight ? h->omegaRight : h->omegaLeft;
-          Vec2 wv = b->GetWorldVector(Vec2(t[0], t[1]));
-          // b2Vec2 / _world_scale / time_step, then * _world_scale: float32 ops in pybox2d
-          Vec2 lv(wv.x / 25.0f, wv.y / 25.0f);
-          lv.Set(lv.x / dtf, lv.y / dtf);
-          lv.Set(lv.x * 25.0f, lv.y * 25.0f);
-          b->SetAngularVelocity(w_);
-          b->SetLinearVelocity(lv);
-        } break;
-        case KB_KILOBOT_SIMPLE_PHOTOTAXIS: {  // :191-203
-          double mx = kc.lightGrad[0], my = kc.lightGrad[1];
-          double n = std::sqrt(mx * mx + my * my);
-          if (n > 0.01) {
-            mx = mx / n * 0.01;
-            my = my / n * 0.01;
-          }
-          mx *= 25.0;
-          my *= 25.0;
-          b->SetLinearVelocity(Vec2((float)mx, (float)my));
-          b->linearDamping = .0f;
-        } break;
-        case KB_KILOBOT_ACCELERATION:  // :294-300
-          kc.velocity[0] += kc.acceleration[0] * dt;
-          kc.velocity[1] += kc.acceleration[1] * dt;
-          kc.velocity[0] = kc.velocity[0] > .0 ? kc.velocity[0] : .0;
-          kc.velocity[1] = kc.velocity[1] > -0.5 * M_PI ? kc.velocity[1] : -0.5 * M_PI;
-          kc.velocity[0] = kc.velocity[0] < 0.01 ? kc.velocity[0] : 0.01;
-          kc.velocity[1] = kc.velocity[1] < 0.5 * M_PI ? kc.velocity[1] : 0.5 * M_PI;
-          // fallthrough
-        case KB_KILOBOT_VELOCITY: {  // :253-258
-          double ang = (double)b->sweep.a;
-          double lx, ly;  // np.cos/np.sin via the shared double sincos (kbo_math.h)
-          SinCosD(ang, &ly, &lx);
-          lx *= kc.velocity[0] * 25.0;
-          ly *= kc.velocity[0] * 25.0;
-          b->SetLinearVelocity(Vec2((float)lx, (float)ly));
-          b->SetAngularVelocity((float)kc.velocity[1]);
-        } break;
-        default: break;
-      }
-    }
+    for (int k = 0; k < N; ++k) RunController(h, e->ctrl[k], e->bodies[M + k], dtf, dt);
     w->Step(dtf, sc.desc.velocity_iterations, sc.desc.position_iterations);  // :187
   }
   for (Body* b : e->bodies) {
@@ -754,6 +756,80 @@ void kbo_libm_sincosf(const float* a, float* s, float* c, int64_t n) {
     s[i] = sinf(a[i]);
     c[i] = cosf(a[i]);
   }
+}
+
+
+// ---- test hooks: evaluate single pieces of the Python-side restatement against golden vectors ----
+// light.value_and_gradients at npts points for a (composite) light: state laid out like obs_light
+void kbo_eval_light(const KbLightDef* defs, int32_t n, const double* state, const double* pts, int32_t npts,
+                    double* value, double* grad) {
+  for (int i = 0; i < npts; ++i) {
+    double v = 0.0, gx = 0.0, gy = 0.0, best = 0.0;
+    int off = 0;
+    for (int l = 0; l < n; ++l) {
+      LightState ls;
+      if (defs[l].type == KB_LIGHT_LINEAR) ls.angle = state[off];
+      else { ls.pos[0] = state[off]; ls.pos[1] = state[off + 1]; }
+      double vv, g0, g1;
+      LightValueGrad(defs[l], ls, pts[2 * i], pts[2 * i + 1], &vv, &g0, &g1);
+      v += vv;
+      if (l == 0 || vv > best) { best = vv; gx = g0; gy = g1; }
+      off += LightStateDim(defs[l]);
+    }
+    value[i] = v;
+    grad[2 * i] = gx;
+    grad[2 * i + 1] = gy;
+  }
+}
+
+// light.step: `substeps` calls with the same action; trace[substeps][dim]
+void kbo_light_step(const KbLightDef* def, double* state, const double* action, int32_t substeps, double* trace) {
+  LightState ls;
+  const int dim = LightStateDim(*def);
+  if (def->type == KB_LIGHT_LINEAR) ls.angle = state[0];
+  else { ls.pos[0] = state[0]; ls.pos[1] = state[1]; if (dim == 4) { ls.vel[0] = state[2]; ls.vel[1] = state[3]; } }
+  for (int s = 0; s < substeps; ++s) {
+    LightStep(*def, &ls, action, 1. / 10);
+    double* o = trace + (size_t)s * dim;
+    if (def->type == KB_LIGHT_LINEAR) o[0] = ls.angle;
+    else { o[0] = ls.pos[0]; o[1] = ls.pos[1]; if (dim == 4) { o[2] = ls.vel[0]; o[3] = ls.vel[1]; } }
+  }
+  if (def->type == KB_LIGHT_LINEAR) state[0] = ls.angle;
+  else { state[0] = ls.pos[0]; state[1] = ls.pos[1]; if (dim == 4) { state[2] = ls.vel[0]; state[3] = ls.vel[1]; } }
+}
+
+// Kilobot.step on a free body at a fixed pose: `calls` controller calls, each fed (value, gx, gy);
+// out[calls][3] = linearVelocity.x, linearVelocity.y, angularVelocity as handed to Box2D
+void kbo_controller_trace(int32_t kind, float px, float py, float angle, const double* vel, const double* feed, int32_t calls,
+                          float* out) {
+  Handle h;
+  ComputeMotorConstants(&h, 1. / 10);
+  World w;
+  w.CreateTable(-1000.f, -1000.f, 1000.f, 1000.f, 0, 0.2f);
+  Body* b = w.CreateBody(px, py, angle, 0.8f, 0.8f);
+  KilobotCtrl kc;
+  kc.kind = kind;
+  if (vel) { kc.velocity[0] = vel[0]; kc.velocity[1] = vel[1]; }
+  for (int i = 0; i < calls; ++i) {
+    kc.lightValue = feed[3 * i];
+    kc.lightGrad[0] = feed[3 * i + 1];
+    kc.lightGrad[1] = feed[3 * i + 2];
+    RunController(&h, kc, b, 0.1f, 1. / 10);
+    out[3 * i] = b->linearVelocity.x;
+    out[3 * i + 1] = b->linearVelocity.y;
+    out[3 * i + 2] = b->angularVelocity;
+  }
+}
+
+// Kilobot.light_sensor_pos for a PhototaxisKilobot at the given pose (SI units in and out)
+void kbo_sensor_pos(double x, double y, double angle, double* out) {
+  Xf xf;
+  xf.p.Set((float)(25.0 * x), (float)(25.0 * y));
+  xf.q.Set((float)angle);
+  Vec2 lp((float)(25.0 * 0.0), (float)(25.0 * -0.0165));
+  Vec2 wp = Mul(xf, lp);
+  out[0] = (double)wp.x / 25.0;
+  out[1] = (double)wp.y / 25.0;
 }
 
 }  // extern "C"
