@@ -11,6 +11,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -21,18 +22,23 @@
 namespace kb {
 
 // ----------------------------------------------------------------------------------- kernels
+#define KB_BLOCK 64   /* threads per block: two warps; envs per block = KB_BLOCK / LPE */
+
+// The batch is padded to a whole number of blocks (numEnvs <= grid * EPB): every lane of the step kernel owns
+// a real environment, so the groups of a warp can run in lock step.  Padding envs replicate the inputs of the
+// last real env and never write outputs.
 template <int LPE>
-__global__ void __launch_bounds__(128) kb_step_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(KB_BLOCK) kb_step_kernel(const __grid_constant__ KernelArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
-  constexpr int EPB = 128 / LPE;
+  constexpr int EPB = KB_BLOCK / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
-  if (env >= a.numEnvs) return;
-  Sim<LPE> s(a.L);
+  const int envIn = min(env, a.numEnvs - 1);
+  Sim<LPE, true> s(a.L);
   s.g.init();
   s.sm = smem + (size_t)slot * a.L.smemWords;
   s.blob = a.blobs + (size_t)env * a.L.blobWords;
-  const int scene = a.envScene ? a.envScene[env] : 0;
+  const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * a.L.Pp;
   s.bc = a.bodies + (size_t)scene * a.L.Bp;
   s.lights = a.lights;
@@ -40,37 +46,40 @@ __global__ void __launch_bounds__(128) kb_step_kernel(const __grid_constant__ Ke
   s.loadState();
   s.initScratch();
   const int A = a.actionMode == KB_ACTION_KILOBOTS ? 2 * a.L.N : a.L.A;
-  const double* act = a.action ? a.action + (size_t)env * A : nullptr;
+  const double* act = a.action ? a.action + (size_t)envIn * A : nullptr;
   if (a.actionMode == KB_ACTION_KILOBOTS) s.setKilobotActions(act);
+  s.g.usync();
   for (int step = 0; step < a.L.stepsPerAction; ++step) {
     if (a.actionMode == KB_ACTION_LIGHT && act && a.L.numLights > 0) s.lightStep(act);
     s.senseControl();
+    s.g.usync();
     s.worldStep();
   }
-  s.gather(a, env);
+  if (env < a.numEnvs) s.gather(a, env);
   s.storeState();
 }
 
 template <int LPE>
-__global__ void __launch_bounds__(128) kb_reset_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(KB_BLOCK) kb_reset_kernel(const __grid_constant__ KernelArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
-  constexpr int EPB = 128 / LPE;
+  constexpr int EPB = KB_BLOCK / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
-  if (env >= a.numEnvs) return;
-  if (a.mask && !a.mask[env]) return;
+  const int envIn = min(env, a.numEnvs - 1);
+  if (a.mask && !a.mask[envIn]) return;
   const Layout& L = a.L;
-  Sim<LPE> s(a.L);
+  Sim<LPE, false> s(a.L);
   s.g.init();
   s.sm = smem + (size_t)slot * L.smemWords;
   s.blob = a.blobs + (size_t)env * L.blobWords;
-  const int scene = a.envScene ? a.envScene[env] : 0;
+  const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * L.Pp;
   s.bc = a.bodies + (size_t)scene * L.Bp;
   s.lights = a.lights;
   s.S = L.B;
   const int lane = s.g.lane;
   for (int i = lane; i < L.stateWords; i += LPE) s.sm[i] = 0u;
+  for (int i = lane; i < 2 * KB_NUM_COUNTERS; i += LPE) reinterpret_cast<uint32_t*>(s.blob)[L.oCnt + i] = 0u;
   s.g.sync();
   if (lane == 0) {
     s.hdr(H_NC) = 0u;
@@ -79,7 +88,7 @@ __global__ void __launch_bounds__(128) kb_reset_kernel(const __grid_constant__ K
   }
   // light.__init__ / MomentumLight(velocity=...) / GradientLight(angle=...)
   if (a.lightInit)
-    for (int i = lane; i < L.L; i += LPE) s.lightState()[i] = a.lightInit[(size_t)env * L.L + i];
+    for (int i = lane; i < L.L; i += LPE) s.lightState()[i] = a.lightInit[(size_t)envIn * L.L + i];
   // controllers: PhototaxisKilobot.__init__ lib/kilobot.py:307-316 (threshold -inf, turn_left)
   for (int k = lane; k < L.N; k += LPE) {
     double* c = s.ctrl(k);
@@ -88,13 +97,13 @@ __global__ void __launch_bounds__(128) kb_reset_kernel(const __grid_constant__ K
     if (kind == KB_KILOBOT_PHOTOTAXIS) {
       c[0] = __longlong_as_double(0xFFF0000000000000LL);  // -inf
     } else if ((kind == KB_KILOBOT_VELOCITY || kind == KB_KILOBOT_ACCELERATION) && a.kbVel) {
-      c[0] = a.kbVel[((size_t)env * L.N + k) * 2 + 0];
-      c[1] = a.kbVel[((size_t)env * L.N + k) * 2 + 1];
+      c[0] = a.kbVel[((size_t)envIn * L.N + k) * 2 + 0];
+      c[1] = a.kbVel[((size_t)envIn * L.N + k) * 2 + 1];
     }
   }
   // bodies: b2World::CreateBody + CreateFixture (lib/body.py:32-38)
   for (int b = lane; b < L.B; b += LPE) {
-    const double* p = a.pose + ((size_t)env * L.B + b) * 3;
+    const double* p = a.pose + ((size_t)envIn * L.B + b) * 3;
     const float x = (float)(25.0 * p[0]);
     const float y = (float)(25.0 * p[1]);
     const float ang = (float)p[2];
@@ -127,30 +136,30 @@ __global__ void __launch_bounds__(128) kb_reset_kernel(const __grid_constant__ K
   mlo = s.g.red_or(mlo);
   mhi = s.g.red_or(mhi);
   if (lane == 0) {
-    s.sm[L.sMoved] = mlo;
-    s.sm[L.sMoved + 1] = mhi;
+    s.hdr(H_MOVED) = mlo;
+    s.hdr(H_MOVED + 1) = mhi;
   }
   s.g.sync();
   s.findNewContacts();  // b2World::Step: m_flags & e_newFixture -> FindNewContacts
   s.worldStep();        // kilobots_env.py:157 "step to resolve"
-  if (lane == 0 && a.status) a.status[env] = (int32_t)s.hdr(H_STATUS);
+  if (lane == 0 && a.status && env < a.numEnvs) a.status[env] = (int32_t)s.hdr(H_STATUS);
   s.storeState();
 }
 
 // Body.set_pose (lib/body.py:67-69) -> b2Body::SetTransform
 template <int LPE>
-__global__ void __launch_bounds__(128) kb_setpose_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(KB_BLOCK) kb_setpose_kernel(const __grid_constant__ KernelArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
-  constexpr int EPB = 128 / LPE;
+  constexpr int EPB = KB_BLOCK / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
-  if (env >= a.numEnvs) return;
+  const int envIn = min(env, a.numEnvs - 1);
   const Layout& L = a.L;
-  Sim<LPE> s(a.L);
+  Sim<LPE, false> s(a.L);
   s.g.init();
   s.sm = smem + (size_t)slot * L.smemWords;
   s.blob = a.blobs + (size_t)env * L.blobWords;
-  const int scene = a.envScene ? a.envScene[env] : 0;
+  const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * L.Pp;
   s.bc = a.bodies + (size_t)scene * L.Bp;
   s.lights = a.lights;
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(128) kb_setpose_kernel(const __grid_constant__
   for (int b = s.g.lane; b <= L.B; b += LPE) s.isl(b) = -1;
   s.g.sync();
   for (int b = s.g.lane; b < L.B; b += LPE) {
-    const double* p = a.pose + ((size_t)env * L.B + b) * 3;
+    const double* p = a.pose + ((size_t)envIn * L.B + b) * 3;
     const float x = (float)(p[0] * 25.0);
     const float y = (float)(p[1] * 25.0);
     const float ang = (float)p[2];
@@ -174,7 +183,7 @@ __global__ void __launch_bounds__(128) kb_setpose_kernel(const __grid_constant__
     s.pos4(b) = pos;
     s.xf4(b) = make_float4(x, y, xf.q.s, xf.q.c);
     s.sweep4(b) = make_float4(c.x, c.y, ang, 0.0f);
-    reinterpret_cast<float2*>(s.sm + L.sSweep + 4 * (L.B + 1))[b] = make_float2(xf.q.s, xf.q.c);
+    s.oldq(b) = make_float2(xf.q.s, xf.q.c);
     s.isl(b) = 0;
   }
   s.g.sync();
@@ -207,6 +216,8 @@ struct Handle {
   int envsPerBlock = 4;
   size_t smemBytes = 0;
 };
+
+static int launchGrid(const Handle* h) { return (h->numEnvs + h->envsPerBlock - 1) / h->envsPerBlock; }
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -468,6 +479,10 @@ static int buildScene(const KbSceneDesc& sd, int Bp, int Pp, std::vector<ProxyCo
     bcst.lcy = lc.y;
   }
   sc->numProxies = p;
+  for (int q = p; q < Pp; ++q) {  // unused slots (scenes with fewer fixtures): inert table proxies that never overlap
+    (*proxies)[q].body = B;
+    (*proxies)[q].type = SHAPE_EDGE;
+  }
   sc->wallEdges = sd.wall_edges;
   sc->rewardConst = sd.reward_const;
   return KB_OK;
@@ -509,7 +524,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   const KbSceneDesc& s0 = scenes[0];
   const int B = s0.num_bodies, M = s0.num_objects, N = B - M;
   if (B < 1 || M < 0 || N < 0) return fail(KB_ERR_INVALID, "kb_create: bad body counts");
-  if (B > KB_MAX_BODIES) return fail(KB_ERR_CAPACITY, "kb_create: more than 63 bodies per env is not supported by the warp-per-env kernel");
+  if (B > KB_MAX_BODIES) return fail(KB_ERR_CAPACITY, "kb_create: more than 62 bodies per env is not supported by the warp-per-env kernel");
   if (s0.num_lights > KB_MAX_LIGHTS) return fail(KB_ERR_INVALID, "kb_create: too many lights");
   int P = 0;
   for (int s = 0; s < num_scenes; ++s) {
@@ -538,42 +553,69 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   L.Bp = B + 1;
   L.Pp = P;
   L.Cmax = round4(max_contacts > 0 ? max_contacts : std::min(P * (P - 1) / 2, 8 * B + 32));
-  L.Kmax = round4(std::min(L.Cmax, std::max(16, 3 * B + 16)));
+  if (L.Cmax > 65535) L.Cmax = 65532;
+  L.Kmax = round4(std::min(std::min(L.Cmax, 3 * B + 16), (int)KB_MAX_SOLVER));
+  L.KW = (L.Kmax + 31) / 32;
+  {
+    // general constraints can only arise between proxies that are not frictionless circles-with-zero-restitution
+    // partners; a safe bound is every pair of object proxies plus object proxies against the table edges.  The
+    // TOI mini-island (one body against the table) uses the same records.
+    int maxObjProxies = 0, maxWall = 0;
+    for (int s = 0; s < num_scenes; ++s) {
+      int op = 0;
+      for (int b = 0; b < M; ++b) op += scenes[s].bodies[b].num_fixtures;
+      maxObjProxies = std::max(maxObjProxies, op);
+      maxWall = std::max(maxWall, (int)scenes[s].wall_edges);
+    }
+    bool allKilobotsFrictionless = true;
+    for (int s = 0; s < num_scenes; ++s)
+      for (int b = M; b < B; ++b)
+        for (int f = 0; f < scenes[s].bodies[b].num_fixtures; ++f) {
+          const KbFixtureDef& fd = scenes[s].bodies[b].fixtures[f];
+          if (fd.friction != 0.0f || fd.restitution != 0.0f || fd.shape != KB_SHAPE_CIRCLE) allKilobotsFrictionless = false;
+        }
+    int gen = maxObjProxies * (maxObjProxies - 1) / 2 + maxObjProxies * maxWall;
+    if (!allKilobotsFrictionless) gen = L.Kmax;
+    L.Gmax = std::min(L.Kmax, std::max(8, gen));
+  }
   L.numLights = s0.num_lights;
   for (int l = 0; l < s0.num_lights; ++l) {
     L.L += lightStateDim(s0.lights[l].type);
     L.A += lightActionDim(s0.lights[l].type);
   }
   int o = 0;
-  L.oHdr = o; o += 8;
-  L.oCnt = o; o += 2 * KB_NUM_COUNTERS;
+  L.oHdr = o; o += H_WORDS;
   L.oLight = o; o += round4(2 * std::max(L.L, 1));
-  L.oCtrl = o; o += round4(8 * std::max(N, 1));
   L.oPos = o; o += 4 * L.Bp;
   L.oVel = o; o += 4 * L.Bp;
   L.oXf = o; o += 4 * L.Bp;
   L.oFat = o; o += 4 * L.Pp;
-  L.oPair = o; o += L.Cmax;
-  L.oInfo = o; o += L.Cmax;
+  L.oCw = o; o += L.Cmax;
   L.stateWords = round4(o);
-  L.oMan = L.stateWords;
-  L.blobWords = L.stateWords + MR_WORDS * L.Cmax;
   o = L.stateWords;
-  L.sSweep = o; o += round4(6 * L.Bp);
+  L.oCnt = o; o += 2 * KB_NUM_COUNTERS;
+  L.oCtrl = o; o += round4(8 * std::max(N, 1));
+  L.oMan = o; o += MR_WORDS * L.Cmax;
+  L.oGen = o; o += GR_WORDS * L.Gmax;
+  L.oToi = o; o += L.Cmax;
+  L.blobWords = round4(o);
+  o = L.stateWords;
+  L.sSweep = o; o += 4 * L.Bp;
+  L.sOldQ = o; o += round4(2 * L.Bp);
   L.sBc = o; o += 4 * L.Bp;
   L.sIsl = o; o += round4(L.Bp);
-  L.sIslMin = o; o += round4(L.Bp);
+  L.sIslFlag = o; o += round4(L.Bp);
   L.sStack = o; o += round4(L.Bp);
   L.sLastLvl = o; o += round4(L.Bp);
   L.sAdj = o; o += round4(2 * L.Pp);
-  L.sMoved = L.oHdr + 4;  // persistent: SetTransform may buffer moves between steps
-  L.sTlist = o; o += L.Kmax;
-  L.sOrder = o; o += 2 * L.Kmax;
-  L.sLvl = o; o += L.Kmax;
-  L.sLvlOff = o; o += round4(2 * (L.Kmax + 2));
-  L.sEslot = o; o += L.Kmax;
-  L.sPool = o; o += POOL_FIELDS * L.Kmax;
-  L.sToi = o; o += L.Cmax;
+  L.sPb = o; o += round4((L.Pp + 3) / 4);
+  L.sBmask = o; o += round4(L.Bp * L.KW);
+  L.sTl = o; o += L.Kmax;
+  L.sOrd = o; o += L.Kmax;
+  L.sEnt = o; o += L.Kmax;
+  L.sEntC = o; o += round4((L.Kmax + 1) / 2);
+  L.sLvlTab = o; o += round4(L.Kmax + 2);
+  L.sRec = o; o += 8 * L.Kmax;
   L.sMisc = o; o += 8;
   L.smemWords = round4(o);
   L.stepsPerAction = s0.steps_per_action;
@@ -600,7 +642,15 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     L.transLeft[1] = (float)((legRight[1] - (s * legRight[0] + c * legRight[1])) * 25.0);
     L.omegaLeft = (float)av;
   }
-  h->envsPerBlock = 4;
+  {
+    int lpe = B <= 6 ? 4 : (B <= 24 ? 8 : (B <= 40 ? 16 : 32));
+    if (const char* ev = getenv("KB_LANES_PER_ENV")) {
+      const int v = atoi(ev);
+      if (v == 4 || v == 8 || v == 16 || v == 32) lpe = v;
+    }
+    L.lanesPerEnv = lpe;
+  }
+  h->envsPerBlock = KB_BLOCK / L.lanesPerEnv;
   h->smemBytes = (size_t)h->envsPerBlock * L.smemWords * 4;
   if (h->smemBytes > (size_t)prop.sharedMemPerBlockOptin) {
     delete h;
@@ -651,7 +701,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     CUDA_TRY(cudaMalloc(&h->dEnvScene, sizeof(int32_t) * num_envs));
     CUDA_TRY(cudaMemcpy(h->dEnvScene, env_scene, sizeof(int32_t) * num_envs, cudaMemcpyHostToDevice));
   }
-  const size_t blobBytes = (size_t)num_envs * L.blobWords * 4;
+  const size_t blobBytes = (size_t)launchGrid(h) * h->envsPerBlock * L.blobWords * 4;  // padded to whole blocks
   CUDA_TRY(cudaMalloc(&h->dBlobs, blobBytes));
   CUDA_TRY(cudaMemset(h->dBlobs, 0, blobBytes));
   const int Amax = std::max(std::max(L.A, 2 * N), 1);
@@ -662,9 +712,19 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   CUDA_TRY(cudaMalloc(&h->dReward, sizeof(float) * num_envs));
   CUDA_TRY(cudaMalloc(&h->dDone, num_envs));
   CUDA_TRY(cudaMalloc(&h->dStatus, sizeof(int32_t) * num_envs));
-  CUDA_TRY(cudaFuncSetAttribute(kb_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(kb_reset_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(kb_setpose_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+#define KB_SET_SMEM(LPE)                                                                                            \
+  case LPE:                                                                                                          \
+    CUDA_TRY(cudaFuncSetAttribute(kb_step_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));   \
+    CUDA_TRY(cudaFuncSetAttribute(kb_reset_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));  \
+    CUDA_TRY(cudaFuncSetAttribute(kb_setpose_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes)); \
+    break;
+  switch (L.lanesPerEnv) {
+    KB_SET_SMEM(4)
+    KB_SET_SMEM(8)
+    KB_SET_SMEM(16)
+    KB_SET_SMEM(32)
+  }
+#undef KB_SET_SMEM
   *out = reinterpret_cast<KbHandle*>(h);
   return KB_OK;
 }
@@ -695,7 +755,13 @@ int kb_get_dims(const KbHandle* hh, KbDims* d) {
   return KB_OK;
 }
 
-static int launchGrid(const Handle* h) { return (h->numEnvs + h->envsPerBlock - 1) / h->envsPerBlock; }
+#define KB_LAUNCH(kernel, h, st, a)                                                               \
+  switch ((h)->L.lanesPerEnv) {                                                                   \
+    case 4: kernel<4><<<launchGrid(h), KB_BLOCK, (h)->smemBytes, (st)>>>(a); break;               \
+    case 8: kernel<8><<<launchGrid(h), KB_BLOCK, (h)->smemBytes, (st)>>>(a); break;               \
+    case 16: kernel<16><<<launchGrid(h), KB_BLOCK, (h)->smemBytes, (st)>>>(a); break;             \
+    default: kernel<32><<<launchGrid(h), KB_BLOCK, (h)->smemBytes, (st)>>>(a); break;             \
+  }
 
 int kb_reset(KbHandle* hh, const uint8_t* mask, const double* body_pose, const double* light_state,
              const double* kb_velocity, void* stream) {
@@ -710,7 +776,7 @@ int kb_reset(KbHandle* hh, const uint8_t* mask, const double* body_pose, const d
   a.lightInit = light_state;
   a.kbVel = kb_velocity;
   a.status = h->dStatus;
-  kb_reset_kernel<32><<<launchGrid(h), 128, h->smemBytes, (cudaStream_t)stream>>>(a);
+  KB_LAUNCH(kb_reset_kernel, h, (cudaStream_t)stream, a);
   CUDA_TRY(cudaGetLastError());
   return KB_OK;
 }
@@ -732,7 +798,7 @@ int kb_step(KbHandle* hh, const double* action, int32_t action_mode, float* obs_
   a.reward = reward;
   a.done = done;
   a.status = status;
-  kb_step_kernel<32><<<launchGrid(h), 128, h->smemBytes, (cudaStream_t)stream>>>(a);
+  KB_LAUNCH(kb_step_kernel, h, (cudaStream_t)stream, a);
   CUDA_TRY(cudaGetLastError());
   return KB_OK;
 }
@@ -813,7 +879,7 @@ int kb_set_poses(KbHandle* hh, const double* body_pose) {
   KernelArgs a;
   fillArgs(h, &a);
   a.pose = d;
-  kb_setpose_kernel<32><<<launchGrid(h), 128, h->smemBytes>>>(a);
+  KB_LAUNCH(kb_setpose_kernel, h, (cudaStream_t)0, a);
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(d);
   if (e != cudaSuccess) return fail(KB_ERR_CUDA, cudaGetErrorString(e));
@@ -832,10 +898,10 @@ int kb_get_contacts(KbHandle* hh, int32_t* pairs, int32_t* count) {
     count[e] = nC;
     for (int k = 0; k < nC && k < L.Cmax; ++k) {
       const int i = nC - 1 - k;  // world-list order: newest first
-      const uint32_t pr = w[L.oPair + i], info = w[L.oInfo + i];
+      const uint32_t info = w[L.oCw + i];
       int32_t* o = pairs + ((size_t)e * L.Cmax + k) * 4;
-      o[0] = (int32_t)(pr & 0xFFFF);
-      o[1] = (int32_t)(pr >> 16);
+      o[0] = (int32_t)CW_PA(info);
+      o[1] = (int32_t)CW_PB(info);
       o[2] = (info & CI_TOUCHING) ? 1 : 0;
       o[3] = (int32_t)((info & CI_PC_MASK) >> CI_PC_SHIFT);
     }
@@ -854,7 +920,7 @@ int kb_get_impulses(KbHandle* hh, float* out) {
     const int nC = (int)w[L.oHdr + H_NC];
     for (int k = 0; k < nC && k < L.Cmax; ++k) {
       const int i = nC - 1 - k;
-      const uint32_t info = w[L.oInfo + i];
+      const uint32_t info = w[L.oCw + i];
       const int pc = (int)((info & CI_PC_MASK) >> CI_PC_SHIFT);
       const uint32_t* rec = w + L.oMan + MR_WORDS * i;
       float* o = out + ((size_t)e * L.Cmax + k) * 4;

@@ -1,7 +1,7 @@
-// kb_step.cuh -- one lane group per environment; the whole KilobotsEnv.step
-// (gym_kilobots/envs/kilobots_env.py:161-215) for that environment runs inside one kernel launch with
-// bodies, fat AABBs, contact ids/flags, controllers and the solver's constraint pool resident in
-// shared memory across all sub-steps of the action.
+// kb_step.cuh -- one lane group (4, 8, 16 or 32 lanes of a warp) per environment; the whole
+// KilobotsEnv.step (gym_kilobots/envs/kilobots_env.py:161-215) for that environment runs inside one
+// kernel launch with bodies, fat AABBs, the persistent contact words, the light and the solver's
+// constraint records resident in shared memory across all sub-steps of the action.
 //
 // Phases per sub-step (reference call sites in brackets):
 //   light_step      [lib/light.py:59-75, 300-316, 237-253; kilobots_env.py:171-172]
@@ -13,8 +13,9 @@
 // Ordering contract: the persistent contact array is kept in creation order, so Box2D's LIFO world
 // list / per-body contact lists are "descending array index"; the island DFS, the constraint order
 // and therefore every float32 result follow Box2D's sequential-impulse order exactly.  Within that
-// order, constraints are executed level by level (a level = constraints whose dynamic bodies are
-// disjoint and whose predecessors are done), which is bit-identical to the sequential sweep.
+// order, constraints are executed row by row (a row = constraints of one dependency level whose
+// dynamic bodies are disjoint and whose predecessors are done), which is bit-identical to the
+// sequential sweep.
 #pragma once
 #include "kb_narrow.cuh"
 
@@ -45,8 +46,8 @@ struct KernelArgs {
   const double* kbVel;
 };
 
-// pool field indices (velocity phase)
-#define PF_IDX 0   /* bA | bB<<8 | pointCount<<16 | general<<20 | type<<24 */
+// general-constraint record words (GR_WORDS per record, HBM/L2)
+#define PF_IDX 0   /* bA | bB<<8 | vcPointCount<<16 | type<<24 | pointCount<<28 */
 #define PF_AUX 1   /* contact index | island<<16 */
 #define PF_NX 2
 #define PF_NY 3
@@ -56,20 +57,33 @@ struct KernelArgs {
 #define PF_RBY 7
 #define PF_NMASS 8
 #define PF_NIMP 9
-#define POOL_FIELDS 10
 
-template <int LPE>
+// touching-list word tl[t]: contact index | bA << 16 | bB << 22 | general << 28
+#define TL_GEN (1u << 28)
+// schedule item ent[e]: bA | bB << 6 | island << 12 | general << 18 | row << 24
+#define IT_BA(x) ((int)((x) & 63u))
+#define IT_BB(x) ((int)(((x) >> 6) & 63u))
+#define IT_ISL(x) ((int)(((x) >> 12) & 63u))
+#define IT_GEN (1u << 18)
+#define IT_ROW(x) ((int)((x) >> 24))
+#define IT_NONE 0xFFFFFFFFu
+
+template <int LPE, bool UNI>
 struct Sim {
-  Group<LPE> g;
+  Group<LPE, UNI> g;
   const Layout& L;
   uint32_t* sm;                 // this env's shared memory (words)
-  float* blob;                  // this env's state image in HBM
+  float* blob;                  // this env's state blob in HBM
   const ProxyConst* px;         // scene proxies
   const BodyConst* bc;          // scene bodies
   const LightConst* lights;
   int S;                        // index of the static table in the body arrays (== L.B)
+  // per-launch counter increments (lane 0's copy is flushed to the blob at the end)
+  uint32_t nSub, nCon, nPts, nLvl, nPit, nToi, nTests, nIsl;
 
-  __device__ __forceinline__ Sim(const Layout& l) : L(l) {}
+  __device__ __forceinline__ Sim(const Layout& l) : L(l) {
+    nSub = nCon = nPts = nLvl = nPit = nToi = nTests = nIsl = 0u;
+  }
 
   // ---- typed views into shared memory
   __device__ __forceinline__ float4& pos4(int b) { return reinterpret_cast<float4*>(sm + L.oPos)[b]; }   // cx cy a sleepTime
@@ -77,22 +91,31 @@ struct Sim {
   __device__ __forceinline__ float4& xf4(int b) { return reinterpret_cast<float4*>(sm + L.oXf)[b]; }     // px py qs qc
   __device__ __forceinline__ float4& fat4(int p) { return reinterpret_cast<float4*>(sm + L.oFat)[p]; }   // lx ly ux uy
   __device__ __forceinline__ float4& sweep4(int b) { return reinterpret_cast<float4*>(sm + L.sSweep)[b]; } // c0x c0y a0 alpha0
+  __device__ __forceinline__ float2& oldq(int b) { return reinterpret_cast<float2*>(sm + L.sOldQ)[b]; }  // xf.q at step start
   __device__ __forceinline__ float4& bc4(int b) { return reinterpret_cast<float4*>(sm + L.sBc)[b]; }     // invMass invI lcx lcy
-  __device__ __forceinline__ uint32_t& cpair(int i) { return sm[L.oPair + i]; }
-  __device__ __forceinline__ uint32_t& cinfo(int i) { return sm[L.oInfo + i]; }
+  __device__ __forceinline__ float4& rec4(int i) { return reinterpret_cast<float4*>(sm + L.sRec)[i]; }   // 2 per schedule entry
+  __device__ __forceinline__ uint32_t& cw(int i) { return sm[L.oCw + i]; }
   __device__ __forceinline__ uint32_t& hdr(int i) { return sm[L.oHdr + i]; }
   __device__ __forceinline__ int32_t& isl(int b) { return reinterpret_cast<int32_t*>(sm + L.sIsl)[b]; }
-  __device__ __forceinline__ uint32_t& islflag(int i) { return sm[L.sIslMin + i]; }
+  __device__ __forceinline__ uint32_t& islflag(int i) { return sm[L.sIslFlag + i]; }
   __device__ __forceinline__ uint32_t& misc(int i) { return sm[L.sMisc + i]; }
   __device__ __forceinline__ uint32_t& adj(int p, int hi) { return sm[L.sAdj + 2 * p + hi]; }
-  __device__ __forceinline__ float& pool(int f, int q) { return reinterpret_cast<float*>(sm + L.sPool)[f * L.Kmax + q]; }
-  __device__ __forceinline__ uint32_t& poolu(int f, int q) { return sm[L.sPool + f * L.Kmax + q]; }
-  // general contacts occupy 3 consecutive slots: word w of the 30-word record
-  __device__ __forceinline__ float& gw(int q, int w) { return pool(w % POOL_FIELDS, q + w / POOL_FIELDS); }
+  __device__ __forceinline__ uint32_t& bmask(int b, int w) { return sm[L.sBmask + b * L.KW + w]; }
+  __device__ __forceinline__ uint32_t& tl(int t) { return sm[L.sTl + t]; }
+  __device__ __forceinline__ uint32_t& ord(int p) { return sm[L.sOrd + p]; }
+  __device__ __forceinline__ uint32_t& ent(int e) { return sm[L.sEnt + e]; }
+  __device__ __forceinline__ uint16_t& entC(int e) { return reinterpret_cast<uint16_t*>(sm + L.sEntC)[e]; }
+  __device__ __forceinline__ uint32_t& lvlTab(int l) { return sm[L.sLvlTab + l]; }
+  __device__ __forceinline__ uint32_t& lastLvl(int b) { return sm[L.sLastLvl + b]; }
+  __device__ __forceinline__ int pbody(int p) { return (int)reinterpret_cast<const uint8_t*>(sm + L.sPb)[p]; }
   __device__ __forceinline__ double* lightState() { return reinterpret_cast<double*>(sm + L.oLight); }
-  __device__ __forceinline__ double* ctrl(int k) { return reinterpret_cast<double*>(sm + L.oCtrl) + 4 * k; }
-  __device__ __forceinline__ unsigned long long* counters() { return reinterpret_cast<unsigned long long*>(sm + L.oCnt); }
+  // ---- HBM/L2-resident parts of the blob
+  __device__ __forceinline__ double* ctrl(int k) { return reinterpret_cast<double*>(blob + L.oCtrl) + 4 * k; }
   __device__ __forceinline__ float* manifoldRec(int i) { return blob + L.oMan + MR_WORDS * i; }
+  __device__ __forceinline__ float* toiCache() { return blob + L.oToi; }
+  __device__ __forceinline__ float& pool(int f, int q) { return blob[L.oGen + GR_WORDS * q + f]; }
+  __device__ __forceinline__ uint32_t& poolu(int f, int q) { return reinterpret_cast<uint32_t*>(blob)[L.oGen + GR_WORDS * q + f]; }
+  __device__ __forceinline__ float& gw(int q, int w) { return blob[L.oGen + GR_WORDS * q + w]; }
 
   __device__ __forceinline__ Xf bodyXf(int b) {
     float4 x = xf4(b);
@@ -127,8 +150,20 @@ struct Sim {
     const float4* src = reinterpret_cast<const float4*>(sm);
     const int n4 = L.stateWords >> 2;
     for (int i = g.lane; i < n4; i += LPE) dst[i] = src[i];
+    if (g.lane == 0) {
+      unsigned long long* c = reinterpret_cast<unsigned long long*>(blob + L.oCnt);
+      c[KB_CNT_SUBSTEPS] += nSub;
+      c[KB_CNT_CONTACTS] += nCon;
+      c[KB_CNT_POINTS] += nPts;
+      c[KB_CNT_LEVELS] += nLvl;
+      c[KB_CNT_POS_ITERS] += nPit;
+      c[KB_CNT_TOI_EVENTS] += nToi;
+      c[KB_CNT_PAIR_TESTS] += nTests;
+      c[KB_CNT_ISLANDS] += nIsl;
+    }
   }
-  // scratch that is constant for the launch: body constants, static-table slot, adjacency masks
+  // scratch that is constant for the launch: body constants, static-table slot, proxy->body map,
+  // adjacency masks of the persistent contact list
   __device__ void initScratch() {
     for (int b = g.lane; b <= L.B; b += LPE) {
       if (b < L.B) {
@@ -142,12 +177,13 @@ struct Sim {
         sweep4(b) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
     }
+    for (int p = g.lane; p < L.P; p += LPE) reinterpret_cast<uint8_t*>(sm + L.sPb)[p] = (uint8_t)__ldg(&px[p].body);
     for (int p = g.lane; p < 2 * L.P; p += LPE) sm[L.sAdj + p] = 0u;
     g.sync();
     const int nC = (int)hdr(H_NC);
     for (int i = g.lane; i < nC; i += LPE) {
-      uint32_t pr = cpair(i);
-      int pa = pr & 0xFFFF, pb = pr >> 16;
+      const uint32_t w = cw(i);
+      const int pa = CW_PA(w), pb = CW_PB(w);
       atomicOr(&adj(pa, pb >> 5), 1u << (pb & 31));
       atomicOr(&adj(pb, pa >> 5), 1u << (pa & 31));
     }
@@ -364,7 +400,7 @@ struct Sim {
           mx *= 25.0;
           my *= 25.0;
           setLinearVelocity(b, mk((float)mx, (float)my));
-          // linearDamping = 0: kept as a per-kind constant, see integrateVelocities()
+          // linearDamping = 0: kept as a per-kind constant, see solve()
         } break;
         case KB_KILOBOT_ACCELERATION: {
           const double hpi = 0.5 * 3.141592653589793;
@@ -410,12 +446,11 @@ struct Sim {
 
   // b2Contact::Update for contact i (this lane).  Returns true if touching changed.
   __device__ __forceinline__ bool updateContact(int i) {
-    const uint32_t pr = cpair(i);
-    const int pa = pr & 0xFFFF, pb = pr >> 16;
-    const int bA = __ldg(&px[pa].body), bB = __ldg(&px[pb].body);
-    uint32_t info = cinfo(i);
-    const int oldPC = (info & CI_PC_MASK) >> CI_PC_SHIFT;
-    const bool wasTouching = (info & CI_TOUCHING) != 0u;
+    uint32_t w = cw(i);
+    const int pa = CW_PA(w), pb = CW_PB(w);
+    const int bA = pbody(pa), bB = pbody(pb);
+    const int oldPC = (w & CI_PC_MASK) >> CI_PC_SHIFT;
+    const bool wasTouching = (w & CI_TOUCHING) != 0u;
     Manifold m;
     m.pointCount = 0;
     m.type = 0;
@@ -452,10 +487,10 @@ struct Sim {
       o[2] = make_float4(u2f(m.id[0]), m.px[1], m.py[1], m.ni[1]);
       o[3] = make_float4(m.ti[1], u2f(m.id[1]), u2f((uint32_t)m.type | ((uint32_t)m.pointCount << 8)), 0.0f);
     }
-    info |= CI_ENABLED;
-    info = touching ? (info | CI_TOUCHING) : (info & ~CI_TOUCHING);
-    info = (info & ~CI_PC_MASK) | ((uint32_t)m.pointCount << CI_PC_SHIFT);
-    cinfo(i) = info;
+    w |= CI_ENABLED;
+    w = touching ? (w | CI_TOUCHING) : (w & ~CI_TOUCHING);
+    w = (w & ~CI_PC_MASK) | ((uint32_t)m.pointCount << CI_PC_SHIFT);
+    cw(i) = w;
     return touching != wasTouching;
   }
 
@@ -464,7 +499,6 @@ struct Sim {
   __device__ void collide() {
     const int nC = (int)hdr(H_NC);
     if (nC == 0) return;
-    const uint32_t CI_DESTROY = 1u << 31, CI_DONE = 1u << 30;
     // any sleeping dynamic body?
     bool sleepy = false;
     for (int b = g.lane; b < L.B; b += LPE) sleepy |= !awake(b);
@@ -481,14 +515,14 @@ struct Sim {
         const int i = base + g.lane;
         bool doit = false;
         int pa = 0, pb = 0, bA = S, bB = S;
+        uint32_t w = 0u;
         if (i < nC) {
-          const uint32_t info = cinfo(i);
-          if ((info & CI_DONE) == 0u) {
-            const uint32_t pr = cpair(i);
-            pa = pr & 0xFFFF;
-            pb = pr >> 16;
-            bA = __ldg(&px[pa].body);
-            bB = __ldg(&px[pb].body);
+          w = cw(i);
+          if ((w & CI_DONE) == 0u) {
+            pa = CW_PA(w);
+            pb = CW_PB(w);
+            bA = pbody(pa);
+            bB = pbody(pb);
             if (!anyAsleep) {
               doit = true;
             } else {
@@ -498,20 +532,20 @@ struct Sim {
             }
           }
         }
-        bool wakeEvent = false;
         if (doit) {
           const float4 fa = fat4(pa), fb = fat4(pb);
           // b2TestOverlap
           const bool overlap = !(fb.x - fa.z > 0.0f || fb.y - fa.w > 0.0f || fa.x - fb.z > 0.0f || fa.y - fb.w > 0.0f);
-          uint32_t info = cinfo(i);
+          bool wakeEvent;
           if (!overlap) {
-            wakeEvent = (info & CI_PC_MASK) != 0u;
-            cinfo(i) = info | CI_DESTROY | CI_DONE;
+            wakeEvent = (w & CI_PC_MASK) != 0u;
+            cw(i) = w | CI_DESTROY | CI_DONE;
             atomicAnd(&adj(pa, pb >> 5), ~(1u << (pb & 31)));
             atomicAnd(&adj(pb, pa >> 5), ~(1u << (pa & 31)));
+            anyDestroyed = true;
           } else {
             wakeEvent = updateContact(i);
-            cinfo(i) |= CI_DONE;
+            cw(i) |= CI_DONE;
           }
           if (wakeEvent && anyAsleep) {
             if (bA != S) atomicMax(&wakeAt[bA], i);
@@ -519,14 +553,13 @@ struct Sim {
           }
         }
         progressed |= doit;
-        anyDestroyed |= doit && (cinfo(i) & CI_DESTROY) != 0u;
-        g.sync();
+        if (anyAsleep) g.sync();
       }
       if (!anyAsleep) break;
       if (!g.any(progressed)) break;
     }
+    g.sync();
     if (anyAsleep) {
-      g.sync();
       for (int b = g.lane; b < L.B; b += LPE)
         if (wakeAt[b] >= 0) wake(b);
       g.sync();
@@ -536,30 +569,28 @@ struct Sim {
     int out = 0;
     for (int base = 0; base < nC; base += LPE) {
       const int i = base + g.lane;
-      uint32_t info = 0u, pr = 0u;
+      uint32_t w = 0u;
       bool keep = false;
       if (i < nC) {
-        info = cinfo(i);
-        pr = cpair(i);
-        keep = (info & CI_DESTROY) == 0u;
-        info &= ~(CI_DONE | CI_DESTROY);
+        w = cw(i);
+        keep = (w & CI_DESTROY) == 0u;
+        w &= ~(CI_DONE | CI_DESTROY);
       }
       if (!compact) {
-        if (i < nC) cinfo(i) = info;
+        if (i < nC) cw(i) = w;
         continue;
       }
       const uint32_t m = g.ballot(keep);
       const int dst = out + __popc(m & g.lt());
       float4 r0, r1, r2, r3;
-      const bool moveRec = keep && dst != i && (info & CI_PC_MASK) != 0u;
+      const bool moveRec = keep && dst != i && (w & CI_PC_MASK) != 0u;
       if (moveRec) {
         const float4* rec = reinterpret_cast<const float4*>(manifoldRec(i));
         r0 = rec[0]; r1 = rec[1]; r2 = rec[2]; r3 = rec[3];
       }
       g.sync();
       if (keep) {
-        cinfo(dst) = info;
-        cpair(dst) = pr;
+        cw(dst) = w;
         if (moveRec) {
           float4* rec = reinterpret_cast<float4*>(manifoldRec(dst));
           rec[0] = r0; rec[1] = r1; rec[2] = r2; rec[3] = r3;
@@ -570,33 +601,206 @@ struct Sim {
     }
     if (compact) {
       if (g.lane == 0) hdr(H_NC) = (uint32_t)out;
-      g.sync();
     }
+    g.sync();
   }
 
   // ------------------------------------------------------------------------------ solver
-  // schedule entry e -> (order position p, pool slot q)
-  __device__ __forceinline__ uint32_t& entry(int e) { return sm[L.sEslot + e]; }
-  __device__ __forceinline__ uint32_t& ordC(int p) { return sm[L.sOrder + p]; }            // contact idx | island << 16
-  __device__ __forceinline__ uint32_t& ordB(int p) { return sm[L.sOrder + L.Kmax + p]; }   // bA | bB << 8 | size << 16
-  __device__ __forceinline__ uint32_t& lvlOff(int l) { return sm[L.sLvlOff + l]; }
-
   struct VelBody {
     V2 v;
     float w;
   };
 
-  // b2ContactSolver ctor + InitializeVelocityConstraints for schedule entry e.  fresh == true is the
+  // ---- simple constraints: one manifold point, no friction, no restitution, fixture B a circle
+  // (every contact of a kilobot).  Two float4 records per schedule entry, resident in shared memory:
+  //   velocity phase: rec[2e] = (normal.x, normal.y, normalMass, normalImpulse), rec[2e+1] = (rA.x, rA.y, rB.x, rB.y)
+  //   position phase: rec[2e] = (localNormal, localPoint),                       rec[2e+1] = (radiusA, radiusB, type, -)
+  // b2ContactSolver ctor + InitializeVelocityConstraints
+  __device__ __forceinline__ void initSimple(int e, int ci, uint32_t item) {
+    const int bA = IT_BA(item), bB = IT_BB(item);
+    const uint32_t w = cw(ci);
+    const int pa = CW_PA(w), pb = CW_PB(w);
+    const float4* rec = reinterpret_cast<const float4*>(manifoldRec(ci));
+    const float4 r0 = rec[0], r1 = rec[1];
+    const int type = (int)(f2u(manifoldRec(ci)[MR_TYPE]) & 0xFFu);
+    const float radiusA = __ldg(&px[pa].radius), radiusB = __ldg(&px[pb].radius);
+    const float4 cA4 = pos4(bA), cB4 = pos4(bB);
+    const float4 kA = bc4(bA), kB = bc4(bB);
+    const float mA = kA.x, iA = kA.y, mB = kB.x, iB = kB.y;
+    const V2 cA = mk(cA4.x, cA4.y), cB = mk(cB4.x, cB4.y);
+    // xf from (c, a): q == the body's current xf.q (b2Rot::Set(sweep.a) is what produced it)
+    Xf xfA, xfB;
+    const float4 xa = xf4(bA), xb = xf4(bB);
+    xfA.q.s = xa.z; xfA.q.c = xa.w;
+    xfB.q.s = xb.z; xfB.q.c = xb.w;
+    xfA.p = cA - rmul(xfA.q, mk(kA.z, kA.w));
+    xfB.p = cB - rmul(xfB.q, mk(kB.z, kB.w));
+    // b2WorldManifold::Initialize
+    V2 normal, pt;
+    const V2 lp = mk(r0.z, r0.w), ln = mk(r0.x, r0.y);
+    const V2 mp0 = mk(r1.x, r1.y);
+    if (type == MANIFOLD_CIRCLES) {
+      normal = mk(1.0f, 0.0f);
+      V2 pointA = xmul(xfA, lp);
+      V2 pointB = xmul(xfB, mp0);
+      if (distsq(pointA, pointB) > KB_EPS * KB_EPS) {
+        normal = pointB - pointA;
+        normalize(normal);
+      }
+      V2 a = pointA + radiusA * normal;
+      V2 b = pointB - radiusB * normal;
+      pt = 0.5f * (a + b);
+    } else {
+      normal = rmul(xfA.q, ln);
+      V2 planePoint = xmul(xfA, lp);
+      V2 clipPoint = xmul(xfB, mp0);
+      V2 a = clipPoint + (radiusA - dot(clipPoint - planePoint, normal)) * normal;
+      V2 b = clipPoint - radiusB * normal;
+      pt = 0.5f * (a + b);
+    }
+    const V2 rA = pt - cA;
+    const V2 rB = pt - cB;
+    const float rnA = cross(rA, normal);
+    const float rnB = cross(rB, normal);
+    const float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+    const float nMass = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+    rec4(2 * e) = make_float4(normal.x, normal.y, nMass, r1.z);  // warm start: dtRatio (== 1) * normalImpulse
+    rec4(2 * e + 1) = make_float4(rA.x, rA.y, rB.x, rB.y);
+  }
+
+  // b2ContactSolver::WarmStart
+  __device__ __forceinline__ void warmStartSimple(int e, uint32_t item) {
+    const int bA = IT_BA(item), bB = IT_BB(item);
+    const float4 r0 = rec4(2 * e), r1 = rec4(2 * e + 1);
+    const float4 kA = bc4(bA), kB = bc4(bB);
+    float4 vA = vel4(bA), vB = vel4(bB);
+    const V2 normal = mk(r0.x, r0.y);
+    const V2 tangent = cross(normal, 1.0f);
+    const V2 rA = mk(r1.x, r1.y), rB = mk(r1.z, r1.w);
+    const V2 P = r0.w * normal + 0.0f * tangent;
+    vA.z -= kA.y * cross(rA, P);
+    vA.x = vA.x - kA.x * P.x;
+    vA.y = vA.y - kA.x * P.y;
+    vB.z += kB.y * cross(rB, P);
+    vB.x = vB.x + kB.x * P.x;
+    vB.y = vB.y + kB.x * P.y;
+    vel4(bA) = vA;  // the static slot receives +0 velocities (invMass = invI = 0): harmless
+    vel4(bB) = vB;
+  }
+
+  // b2ContactSolver::SolveVelocityConstraints (the tangent row contributes exactly zero: friction == 0)
+  __device__ __forceinline__ void solveVelocitySimple(int e, uint32_t item) {
+    const int bA = IT_BA(item), bB = IT_BB(item);
+    const float4 r0 = rec4(2 * e), r1 = rec4(2 * e + 1);
+    const float4 kA = bc4(bA), kB = bc4(bB);
+    float4 a4 = vel4(bA), b4 = vel4(bB);
+    const V2 normal = mk(r0.x, r0.y);
+    const V2 rA0 = mk(r1.x, r1.y), rB0 = mk(r1.z, r1.w);
+    const V2 Av = mk(a4.x, a4.y), Bv = mk(b4.x, b4.y);
+    V2 dv = Bv + cross(b4.z, rB0) - Av - cross(a4.z, rA0);
+    float vn = dot(dv, normal);
+    float ni = r0.w;
+    float lambda = -r0.z * (vn - 0.0f);
+    float newImpulse = b2max(ni + lambda, 0.0f);
+    lambda = newImpulse - ni;
+    V2 P = lambda * normal;
+    const V2 Av2 = Av - kA.x * P;
+    a4.z -= kA.y * cross(rA0, P);
+    const V2 Bv2 = Bv + kB.x * P;
+    b4.z += kB.y * cross(rB0, P);
+    a4.x = Av2.x; a4.y = Av2.y;
+    b4.x = Bv2.x; b4.y = Bv2.y;
+    vel4(bA) = a4;
+    vel4(bB) = b4;
+    reinterpret_cast<float*>(&rec4(2 * e))[3] = newImpulse;
+  }
+
+  // b2ContactSolver::StoreImpulses, then re-purpose the records for the position solver
+  __device__ __forceinline__ void storeSimple(int e, int ci) {
+    float* rec = manifoldRec(ci);
+    rec[MR_P0N] = rec4(2 * e).w;
+    const float4 r0 = reinterpret_cast<const float4*>(rec)[0];
+    const uint32_t tp = f2u(rec[MR_TYPE]);
+    const uint32_t w = cw(ci);
+    rec4(2 * e) = r0;
+    rec4(2 * e + 1) = make_float4(__ldg(&px[CW_PA(w)].radius), __ldg(&px[CW_PB(w)].radius), u2f(tp & 0xFFu), 0.0f);
+  }
+
+  // one constraint of b2ContactSolver::SolvePositionConstraints.  Returns false if the separation is
+  // below -3 * linearSlop (island not yet solved).
+  __device__ __forceinline__ bool solvePositionSimple(int e, uint32_t item) {
+    const int bA = IT_BA(item), bB = IT_BB(item);
+    const float4 r0 = rec4(2 * e), r1 = rec4(2 * e + 1);
+    const float4 kA = bc4(bA), kB = bc4(bB);
+    const float mA = kA.x, iA = kA.y, mB = kB.x, iB = kB.y;
+    const V2 lcA = mk(kA.z, kA.w), lcB = mk(kB.z, kB.w);
+    float4 pA4 = pos4(bA), pB4 = pos4(bB);
+    V2 cA = mk(pA4.x, pA4.y), cB = mk(pB4.x, pB4.y);
+    float aA = pA4.z, aB = pB4.z;
+    const V2 ln = mk(r0.x, r0.y);
+    const V2 lp = mk(r0.z, r0.w);
+    const float radiusA = r1.x, radiusB = r1.y;
+    const int type = (int)f2u(r1.z);
+    // a rotation is only needed where it multiplies something non-zero (0 * finite == 0 exactly)
+    const bool trigA = bA != S && (type != MANIFOLD_CIRCLES || lp.x != 0.0f || lp.y != 0.0f || lcA.x != 0.0f ||
+                                   lcA.y != 0.0f);
+    const bool trigB = bB != S && (lcB.x != 0.0f || lcB.y != 0.0f);
+    Xf xfA, xfB;
+    if (trigA) xfA.q = rot_set(aA);
+    else { xfA.q.s = 0.0f; xfA.q.c = 1.0f; }
+    if (trigB) xfB.q = rot_set(aB);
+    else { xfB.q.s = 0.0f; xfB.q.c = 1.0f; }
+    xfA.p = cA - rmul(xfA.q, lcA);
+    xfB.p = cB - rmul(xfB.q, lcB);
+    const V2 mpj = mk(0.0f, 0.0f);
+    V2 normal, point;
+    float separation;
+    if (type == MANIFOLD_CIRCLES) {
+      V2 pointA = xmul(xfA, lp);
+      V2 pointB = xmul(xfB, mpj);
+      normal = pointB - pointA;
+      normalize(normal);
+      point = 0.5f * (pointA + pointB);
+      separation = dot(pointB - pointA, normal) - radiusA - radiusB;
+    } else {
+      normal = rmul(xfA.q, ln);
+      V2 planePoint = xmul(xfA, lp);
+      V2 clipPoint = xmul(xfB, mpj);
+      separation = dot(clipPoint - planePoint, normal) - radiusA - radiusB;
+      point = clipPoint;
+    }
+    V2 rA = point - cA;
+    V2 rB = point - cB;
+    const bool ok = separation >= -3.0f * KB_LINEAR_SLOP;
+    float C = b2clamp(KB_BAUMGARTE * (separation + KB_LINEAR_SLOP), -KB_MAX_LINEAR_CORRECTION, 0.0f);
+    float rnA = cross(rA, normal);
+    float rnB = cross(rB, normal);
+    float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+    float impulse = K > 0.0f ? -C / K : 0.0f;
+    V2 P = impulse * normal;
+    cA = cA - mA * P;
+    aA -= iA * cross(rA, P);
+    cB = cB + mB * P;
+    aB += iB * cross(rB, P);
+    if (bA != S) {
+      pA4.x = cA.x; pA4.y = cA.y; pA4.z = aA;
+      pos4(bA) = pA4;
+    }
+    if (bB != S) {
+      pB4.x = cB.x; pB4.y = cB.y; pB4.z = aB;
+      pos4(bB) = pB4;
+    }
+    return ok;
+  }
+
+  // ---- general constraints (two manifold points, friction or restitution: object-object and
+  // object-table contacts, and the TOI mini-island).  Records live in HBM/L2 (GR_WORDS words each);
+  // one lane owns a record for the whole solve, so no cross-lane visibility is needed.
+  // b2ContactSolver ctor + InitializeVelocityConstraints for general slot q.  fresh == true is the
   // TOI island variant: rotations rebuilt from the (corrected) angles, no warm starting.
-  __device__ __forceinline__ void initConstraint(int e, bool fresh = false) {
-    const uint32_t en = entry(e);
-    const int p = en & 0xFFFF, q = en >> 16;
-    const uint32_t oc = ordC(p), ob = ordB(p);
-    const int ci = oc & 0xFFFF;
-    const int bA = ob & 0xFF, bB = (ob >> 8) & 0xFF;
-    const bool general = ((ob >> 16) & 0xFF) > 1;
-    const uint32_t pr = cpair(ci);
-    const int pa = pr & 0xFFFF, pb = pr >> 16;
+  __device__ __noinline__ void initGeneral(int q, int ci, int bA, int bB, uint32_t aux, bool fresh) {
+    const uint32_t w = cw(ci);
+    const int pa = CW_PA(w), pb = CW_PB(w);
     const float4* rec = reinterpret_cast<const float4*>(manifoldRec(ci));
     const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
     const uint32_t tp = f2u(r3.z);
@@ -609,7 +813,6 @@ struct Sim {
     const V2 cA = mk(cA4.x, cA4.y), cB = mk(cB4.x, cB4.y);
     const V2 vA = mk(vA4.x, vA4.y), vB = mk(vB4.x, vB4.y);
     const float wA = vA4.z, wB = vB4.z;
-    // xf from (c, a): q == the body's current xf.q (b2Rot::Set(sweep.a) is what produced it)
     Xf xfA, xfB;
     {
       if (fresh) {
@@ -704,9 +907,9 @@ struct Sim {
         vcPointCount = 1;
       }
     }
-    poolu(PF_IDX, q) = (uint32_t)bA | ((uint32_t)bB << 8) | ((uint32_t)vcPointCount << 16) |
-                       ((uint32_t)(general ? 1 : 0) << 20) | ((uint32_t)type << 24) | ((uint32_t)pointCount << 28);
-    poolu(PF_AUX, q) = oc;
+    poolu(PF_IDX, q) = (uint32_t)bA | ((uint32_t)bB << 8) | ((uint32_t)vcPointCount << 16) | ((uint32_t)type << 24) |
+                       ((uint32_t)pointCount << 28);
+    poolu(PF_AUX, q) = aux;
     pool(PF_NX, q) = normal.x;
     pool(PF_NY, q) = normal.y;
     pool(PF_RAX, q) = rA[0].x;
@@ -715,30 +918,28 @@ struct Sim {
     pool(PF_RBY, q) = rB[0].y;
     pool(PF_NMASS, q) = nMass[0];
     pool(PF_NIMP, q) = fresh ? 0.0f : r1.z;  // warm start: dtRatio (== 1) * normalImpulse
-    if (general) {
-      gw(q, 10) = tMass[0];
-      gw(q, 11) = fresh ? 0.0f : r1.w;  // tangentImpulse
-      gw(q, 12) = bias[0];
-      gw(q, 13) = friction;
-      gw(q, 14) = k11;
-      gw(q, 15) = k12;
-      gw(q, 16) = k22;
-      gw(q, 17) = nm00;
-      gw(q, 18) = nm01;
-      gw(q, 19) = nm11;
-      if (pointCount == 2) {
-        gw(q, 20) = rA[1].x;
-        gw(q, 21) = rA[1].y;
-        gw(q, 22) = rB[1].x;
-        gw(q, 23) = rB[1].y;
-        gw(q, 24) = nMass[1];
-        gw(q, 25) = fresh ? 0.0f : r2.w;  // p1 normalImpulse
-        gw(q, 26) = tMass[1];
-        gw(q, 27) = fresh ? 0.0f : r3.x;  // p1 tangentImpulse
-        gw(q, 28) = bias[1];
-      }
-      gw(q, 29) = nm10;
+    gw(q, 10) = tMass[0];
+    gw(q, 11) = fresh ? 0.0f : r1.w;  // tangentImpulse
+    gw(q, 12) = bias[0];
+    gw(q, 13) = friction;
+    gw(q, 14) = k11;
+    gw(q, 15) = k12;
+    gw(q, 16) = k22;
+    gw(q, 17) = nm00;
+    gw(q, 18) = nm01;
+    gw(q, 19) = nm11;
+    if (pointCount == 2) {
+      gw(q, 20) = rA[1].x;
+      gw(q, 21) = rA[1].y;
+      gw(q, 22) = rB[1].x;
+      gw(q, 23) = rB[1].y;
+      gw(q, 24) = nMass[1];
+      gw(q, 25) = fresh ? 0.0f : r2.w;  // p1 normalImpulse
+      gw(q, 26) = tMass[1];
+      gw(q, 27) = fresh ? 0.0f : r3.x;  // p1 tangentImpulse
+      gw(q, 28) = bias[1];
     }
+    gw(q, 29) = nm10;
   }
 
   __device__ __forceinline__ void loadVel(int b, VelBody& o) {
@@ -754,12 +955,11 @@ struct Sim {
     v[2] = o.w;
   }
 
-  // b2ContactSolver::WarmStart for one constraint
-  __device__ __forceinline__ void warmStartOne(int q) {
+  // b2ContactSolver::WarmStart for one general constraint
+  __device__ __noinline__ void warmStartGeneral(int q) {
     const uint32_t idx = poolu(PF_IDX, q);
     const int bA = idx & 0xFF, bB = (idx >> 8) & 0xFF;
     const int pointCount = (idx >> 16) & 0xF;
-    const bool general = ((idx >> 20) & 1u) != 0u;
     const float4 kA = bc4(bA), kB = bc4(bB);
     const float mA = kA.x, iA = kA.y, mB = kB.x, iB = kB.y;
     VelBody A, Bv;
@@ -770,7 +970,7 @@ struct Sim {
     {
       const V2 rA = mk(pool(PF_RAX, q), pool(PF_RAY, q)), rB = mk(pool(PF_RBX, q), pool(PF_RBY, q));
       const float ni = pool(PF_NIMP, q);
-      const float ti = general ? gw(q, 11) : 0.0f;
+      const float ti = gw(q, 11);
       V2 P = ni * normal + ti * tangent;
       A.w -= iA * cross(rA, P);
       A.v = A.v - mA * P;
@@ -789,12 +989,11 @@ struct Sim {
     storeVel(bB, Bv);
   }
 
-  // b2ContactSolver::SolveVelocityConstraints for one constraint
-  __device__ __forceinline__ void solveVelocityOne(int q) {
+  // b2ContactSolver::SolveVelocityConstraints for one general constraint
+  __device__ __noinline__ void solveVelocityGeneral(int q) {
     const uint32_t idx = poolu(PF_IDX, q);
     const int bA = idx & 0xFF, bB = (idx >> 8) & 0xFF;
     const int pointCount = (idx >> 16) & 0xF;
-    const bool general = ((idx >> 20) & 1u) != 0u;
     const float4 kA = bc4(bA), kB = bc4(bB);
     const float mA = kA.x, iA = kA.y, mB = kB.x, iB = kB.y;
     VelBody A, Bv;
@@ -802,12 +1001,37 @@ struct Sim {
     loadVel(bB, Bv);
     const V2 normal = mk(pool(PF_NX, q), pool(PF_NY, q));
     const V2 rA0 = mk(pool(PF_RAX, q), pool(PF_RAY, q)), rB0 = mk(pool(PF_RBX, q), pool(PF_RBY, q));
-    if (!general) {
-      // frictionless single point: the tangent row contributes exactly zero (friction == 0)
+    const V2 tangent = cross(normal, 1.0f);
+    const float friction = gw(q, 13);
+    V2 rA1 = rA0, rB1 = rB0;
+    if (pointCount == 2) {
+      rA1 = mk(gw(q, 20), gw(q, 21));
+      rB1 = mk(gw(q, 22), gw(q, 23));
+    }
+    // tangent rows first
+    for (int j = 0; j < pointCount; ++j) {
+      const V2 rA = j == 0 ? rA0 : rA1, rB = j == 0 ? rB0 : rB1;
+      const float tMass = j == 0 ? gw(q, 10) : gw(q, 26);
+      const float nImp = j == 0 ? pool(PF_NIMP, q) : gw(q, 25);
+      float& tImp = j == 0 ? gw(q, 11) : gw(q, 27);
+      V2 dv = Bv.v + cross(Bv.w, rB) - A.v - cross(A.w, rA);
+      float vt = dot(dv, tangent) - 0.0f;
+      float lambda = tMass * (-vt);
+      float maxFriction = friction * nImp;
+      float newImpulse = b2clamp(tImp + lambda, -maxFriction, maxFriction);
+      lambda = newImpulse - tImp;
+      tImp = newImpulse;
+      V2 P = lambda * tangent;
+      A.v = A.v - mA * P;
+      A.w -= iA * cross(rA, P);
+      Bv.v = Bv.v + mB * P;
+      Bv.w += iB * cross(rB, P);
+    }
+    if (pointCount == 1) {
       V2 dv = Bv.v + cross(Bv.w, rB0) - A.v - cross(A.w, rA0);
       float vn = dot(dv, normal);
       float ni = pool(PF_NIMP, q);
-      float lambda = -pool(PF_NMASS, q) * (vn - 0.0f);
+      float lambda = -pool(PF_NMASS, q) * (vn - gw(q, 12));
       float newImpulse = b2max(ni + lambda, 0.0f);
       lambda = newImpulse - ni;
       pool(PF_NIMP, q) = newImpulse;
@@ -817,148 +1041,102 @@ struct Sim {
       Bv.v = Bv.v + mB * P;
       Bv.w += iB * cross(rB0, P);
     } else {
-      const V2 tangent = cross(normal, 1.0f);
-      const float friction = gw(q, 13);
-      V2 rA1 = rA0, rB1 = rB0;
-      if (pointCount == 2) {
-        rA1 = mk(gw(q, 20), gw(q, 21));
-        rB1 = mk(gw(q, 22), gw(q, 23));
+      // block solver
+      const float k11 = gw(q, 14), k12 = gw(q, 15), k22 = gw(q, 16);
+      const float nm00 = gw(q, 17), nm01 = gw(q, 18), nm10 = gw(q, 29), nm11 = gw(q, 19);
+      const float nMass1 = pool(PF_NMASS, q), nMass2 = gw(q, 24);
+      V2 a = mk(pool(PF_NIMP, q), gw(q, 25));
+      V2 dv1 = Bv.v + cross(Bv.w, rB0) - A.v - cross(A.w, rA0);
+      V2 dv2 = Bv.v + cross(Bv.w, rB1) - A.v - cross(A.w, rA1);
+      float vn1 = dot(dv1, normal);
+      float vn2 = dot(dv2, normal);
+      V2 b;
+      b.x = vn1 - gw(q, 12);
+      b.y = vn2 - gw(q, 28);
+      // b -= K a ; K.ex = (k11,k12), K.ey = (k12,k22)
+      b = b - mk(k11 * a.x + k12 * a.y, k12 * a.x + k22 * a.y);
+      V2 x;
+      bool found = false;
+      // case 1
+      {
+        V2 t = mk(nm00 * b.x + nm01 * b.y, nm10 * b.x + nm11 * b.y);
+        x = -t;
+        if (x.x >= 0.0f && x.y >= 0.0f) found = true;
       }
-      // tangent rows first
-      for (int j = 0; j < pointCount; ++j) {
-        const V2 rA = j == 0 ? rA0 : rA1, rB = j == 0 ? rB0 : rB1;
-        const float tMass = j == 0 ? gw(q, 10) : gw(q, 26);
-        const float nImp = j == 0 ? pool(PF_NIMP, q) : gw(q, 25);
-        float& tImp = j == 0 ? gw(q, 11) : gw(q, 27);
-        V2 dv = Bv.v + cross(Bv.w, rB) - A.v - cross(A.w, rA);
-        float vt = dot(dv, tangent) - 0.0f;
-        float lambda = tMass * (-vt);
-        float maxFriction = friction * nImp;
-        float newImpulse = b2clamp(tImp + lambda, -maxFriction, maxFriction);
-        lambda = newImpulse - tImp;
-        tImp = newImpulse;
-        V2 P = lambda * tangent;
-        A.v = A.v - mA * P;
-        A.w -= iA * cross(rA, P);
-        Bv.v = Bv.v + mB * P;
-        Bv.w += iB * cross(rB, P);
+      if (!found) {  // case 2
+        x.x = -nMass1 * b.x;
+        x.y = 0.0f;
+        vn2 = k12 * x.x + b.y;
+        if (x.x >= 0.0f && vn2 >= 0.0f) found = true;
       }
-      if (pointCount == 1) {
-        V2 dv = Bv.v + cross(Bv.w, rB0) - A.v - cross(A.w, rA0);
-        float vn = dot(dv, normal);
-        float ni = pool(PF_NIMP, q);
-        float lambda = -pool(PF_NMASS, q) * (vn - gw(q, 12));
-        float newImpulse = b2max(ni + lambda, 0.0f);
-        lambda = newImpulse - ni;
-        pool(PF_NIMP, q) = newImpulse;
-        V2 P = lambda * normal;
-        A.v = A.v - mA * P;
-        A.w -= iA * cross(rA0, P);
-        Bv.v = Bv.v + mB * P;
-        Bv.w += iB * cross(rB0, P);
-      } else {
-        // block solver
-        const float k11 = gw(q, 14), k12 = gw(q, 15), k22 = gw(q, 16);
-        const float nm00 = gw(q, 17), nm01 = gw(q, 18), nm10 = gw(q, 29), nm11 = gw(q, 19);
-        const float nMass1 = pool(PF_NMASS, q), nMass2 = gw(q, 24);
-        V2 a = mk(pool(PF_NIMP, q), gw(q, 25));
-        V2 dv1 = Bv.v + cross(Bv.w, rB0) - A.v - cross(A.w, rA0);
-        V2 dv2 = Bv.v + cross(Bv.w, rB1) - A.v - cross(A.w, rA1);
-        float vn1 = dot(dv1, normal);
-        float vn2 = dot(dv2, normal);
-        V2 b;
-        b.x = vn1 - gw(q, 12);
-        b.y = vn2 - gw(q, 28);
-        // b -= K a ; K.ex = (k11,k12), K.ey = (k12,k22)
-        b = b - mk(k11 * a.x + k12 * a.y, k12 * a.x + k22 * a.y);
-        V2 x;
-        bool found = false;
-        // case 1
-        {
-          V2 t = mk(nm00 * b.x + nm01 * b.y, nm10 * b.x + nm11 * b.y);
-          x = -t;
-          if (x.x >= 0.0f && x.y >= 0.0f) found = true;
-        }
-        if (!found) {  // case 2
-          x.x = -nMass1 * b.x;
-          x.y = 0.0f;
-          vn2 = k12 * x.x + b.y;
-          if (x.x >= 0.0f && vn2 >= 0.0f) found = true;
-        }
-        if (!found) {  // case 3
-          x.x = 0.0f;
-          x.y = -nMass2 * b.y;
-          vn1 = k12 * x.y + b.x;
-          if (x.y >= 0.0f && vn1 >= 0.0f) found = true;
-        }
-        if (!found) {  // case 4
-          x.x = 0.0f;
-          x.y = 0.0f;
-          vn1 = b.x;
-          vn2 = b.y;
-          if (vn1 >= 0.0f && vn2 >= 0.0f) found = true;
-        }
-        if (found) {
-          V2 d = x - a;
-          V2 P1 = d.x * normal;
-          V2 P2 = d.y * normal;
-          A.v = A.v - mA * (P1 + P2);
-          A.w -= iA * (cross(rA0, P1) + cross(rA1, P2));
-          Bv.v = Bv.v + mB * (P1 + P2);
-          Bv.w += iB * (cross(rB0, P1) + cross(rB1, P2));
-          pool(PF_NIMP, q) = x.x;
-          gw(q, 25) = x.y;
-        }
+      if (!found) {  // case 3
+        x.x = 0.0f;
+        x.y = -nMass2 * b.y;
+        vn1 = k12 * x.y + b.x;
+        if (x.y >= 0.0f && vn1 >= 0.0f) found = true;
+      }
+      if (!found) {  // case 4
+        x.x = 0.0f;
+        x.y = 0.0f;
+        vn1 = b.x;
+        vn2 = b.y;
+        if (vn1 >= 0.0f && vn2 >= 0.0f) found = true;
+      }
+      if (found) {
+        V2 d = x - a;
+        V2 P1 = d.x * normal;
+        V2 P2 = d.y * normal;
+        A.v = A.v - mA * (P1 + P2);
+        A.w -= iA * (cross(rA0, P1) + cross(rA1, P2));
+        Bv.v = Bv.v + mB * (P1 + P2);
+        Bv.w += iB * (cross(rB0, P1) + cross(rB1, P2));
+        pool(PF_NIMP, q) = x.x;
+        gw(q, 25) = x.y;
       }
     }
     storeVel(bA, A);
     storeVel(bB, Bv);
   }
 
-  // b2ContactSolver::StoreImpulses, then re-purpose the pool for the position solver
-  __device__ __forceinline__ void storeImpulsesAndPreparePosition(int e) {
-    const uint32_t en = entry(e);
-    const int q = en >> 16;
+  // b2ContactSolver::StoreImpulses, then re-purpose the record for the position solver
+  __device__ __noinline__ void storeGeneral(int q) {
     const uint32_t idx = poolu(PF_IDX, q);
     const uint32_t aux = poolu(PF_AUX, q);
     const int ci = aux & 0xFFFF;
     const int vcPointCount = (idx >> 16) & 0xF;
-    const bool general = ((idx >> 20) & 1u) != 0u;
     float* rec = manifoldRec(ci);
     rec[MR_P0N] = pool(PF_NIMP, q);
-    if (general) {
-      rec[MR_P0T] = gw(q, 11);
-      if (vcPointCount == 2) {
-        rec[MR_P1N] = gw(q, 25);
-        rec[MR_P1T] = gw(q, 27);
-      }
+    rec[MR_P0T] = gw(q, 11);
+    if (vcPointCount == 2) {
+      rec[MR_P1N] = gw(q, 25);
+      rec[MR_P1T] = gw(q, 27);
     }
-    // position data: localNormal, localPoint, radii (+ both local points for general contacts)
+    preparePositionGeneral(q, ci);
+  }
+  // position data: localNormal, localPoint, radii and both manifold points
+  __device__ __forceinline__ void preparePositionGeneral(int q, int ci) {
+    const float* rec = manifoldRec(ci);
     const float4 r0 = reinterpret_cast<const float4*>(rec)[0];
-    const uint32_t pr = cpair(ci);
-    const int pa = pr & 0xFFFF, pb = pr >> 16;
+    const float4 r1 = reinterpret_cast<const float4*>(rec)[1];
+    const float4 r2 = reinterpret_cast<const float4*>(rec)[2];
+    const uint32_t w = cw(ci);
     pool(PF_NX, q) = r0.x;
     pool(PF_NY, q) = r0.y;
     pool(PF_RAX, q) = r0.z;
     pool(PF_RAY, q) = r0.w;
-    pool(PF_RBX, q) = __ldg(&px[pa].radius);
-    pool(PF_RBY, q) = __ldg(&px[pb].radius);
-    if (general) {
-      const float4 r1 = reinterpret_cast<const float4*>(rec)[1];
-      const float4 r2 = reinterpret_cast<const float4*>(rec)[2];
-      gw(q, 10) = r1.x;
-      gw(q, 11) = r1.y;
-      gw(q, 12) = r2.y;
-      gw(q, 13) = r2.z;
-    }
+    pool(PF_RBX, q) = __ldg(&px[CW_PA(w)].radius);
+    pool(PF_RBY, q) = __ldg(&px[CW_PB(w)].radius);
+    gw(q, 10) = r1.x;
+    gw(q, 11) = r1.y;
+    gw(q, 12) = r2.y;
+    gw(q, 13) = r2.z;
   }
 
-  // one constraint of b2ContactSolver::SolvePositionConstraints / SolveTOIPositionConstraints.
+  // one general constraint of b2ContactSolver::SolvePositionConstraints / SolveTOIPositionConstraints.
   // Returns false if any point's separation is below `limit` (island not yet solved).
-  __device__ __forceinline__ bool solvePositionOne(int q, float baumgarte, float limit, int toiA, int toiB) {
+  __device__ __noinline__ bool solvePositionGeneral(int q, float baumgarte, float limit, int toiA, int toiB) {
     const uint32_t idx = poolu(PF_IDX, q);
     const int bA = idx & 0xFF, bB = (idx >> 8) & 0xFF;
-    const bool general = ((idx >> 20) & 1u) != 0u;
     const int type = (idx >> 24) & 0xF;
     const int pointCount = (idx >> 28) & 0xF;
     const float4 kA = bc4(bA), kB = bc4(bB);
@@ -974,10 +1152,7 @@ struct Sim {
     const V2 ln = mk(pool(PF_NX, q), pool(PF_NY, q));
     const V2 lp = mk(pool(PF_RAX, q), pool(PF_RAY, q));
     const float radiusA = pool(PF_RBX, q), radiusB = pool(PF_RBY, q);
-    // a rotation is only needed where it multiplies something non-zero (0 * finite == 0 exactly)
-    const bool trigA = bA != S && (type != MANIFOLD_CIRCLES || lp.x != 0.0f || lp.y != 0.0f || lcA.x != 0.0f ||
-                                   lcA.y != 0.0f || general);
-    const bool trigB = bB != S && (type == MANIFOLD_FACE_B || lcB.x != 0.0f || lcB.y != 0.0f || general);
+    const bool trigA = bA != S, trigB = bB != S;
     bool ok = true;
     for (int j = 0; j < pointCount; ++j) {
       Xf xfA, xfB;
@@ -987,8 +1162,7 @@ struct Sim {
       else { xfB.q.s = 0.0f; xfB.q.c = 1.0f; }
       xfA.p = cA - rmul(xfA.q, lcA);
       xfB.p = cB - rmul(xfB.q, lcB);
-      V2 mpj = mk(0.0f, 0.0f);
-      if (general) mpj = j == 0 ? mk(gw(q, 10), gw(q, 11)) : mk(gw(q, 12), gw(q, 13));
+      const V2 mpj = j == 0 ? mk(gw(q, 10), gw(q, 11)) : mk(gw(q, 12), gw(q, 13));
       V2 normal, point;
       float separation;
       if (type == MANIFOLD_CIRCLES) {
@@ -1037,172 +1211,137 @@ struct Sim {
     return ok;
   }
 
+  // general slot of schedule entry e (kept in the entry's otherwise unused simple record)
+  __device__ __forceinline__ int genSlot(int e) { return (int)sm[L.sRec + 8 * e]; }
+
   // b2World::Solve
   __device__ void solve() {
     const int nC = (int)hdr(H_NC);
     const int B = L.B;
-    unsigned long long* cnt = counters();
-    // ---- touching list in world-list order (descending index)
-    uint32_t* tlist = sm + L.sTlist;
+    const int KW = L.KW;
+    // ---- touching list in world-list order (descending index) and per-body masks over it
+    for (int i = g.lane; i < (B + 1) * KW; i += LPE) sm[L.sBmask + i] = 0u;
+    for (int b = g.lane; b <= B; b += LPE) {
+      isl(b) = -1;
+      lastLvl(b) = 0u;
+    }
+    g.sync();
     int K = 0;
     for (int base = 0; base < nC; base += LPE) {
       const int i = nC - 1 - (base + g.lane);
       bool t = false;
       uint32_t val = 0u;
+      int bA = S, bB = S;
       if (i >= 0) {
-        const uint32_t info = cinfo(i);
-        t = (info & (CI_TOUCHING | CI_ENABLED)) == (CI_TOUCHING | CI_ENABLED);
+        const uint32_t w = cw(i);
+        t = (w & (CI_TOUCHING | CI_ENABLED)) == (CI_TOUCHING | CI_ENABLED);
         if (t) {
-          const uint32_t pr = cpair(i);
-          const int bA = __ldg(&px[pr & 0xFFFF].body), bB = __ldg(&px[pr >> 16].body);
-          val = (uint32_t)i | ((uint32_t)bA << 16) | ((uint32_t)bB << 24);
+          const int pa = CW_PA(w), pb = CW_PB(w);
+          bA = pbody(pa);
+          bB = pbody(pb);
+          const int pc = (w & CI_PC_MASK) >> CI_PC_SHIFT;
+          const float fr = __ldg(&px[pa].friction) * __ldg(&px[pb].friction);
+          const float re = b2max(__ldg(&px[pa].restitution), __ldg(&px[pb].restitution));
+          const bool simple = pc == 1 && fr == 0.0f && re == 0.0f && __ldg(&px[pb].type) == SHAPE_CIRCLE;
+          val = (uint32_t)i | ((uint32_t)bA << 16) | ((uint32_t)bB << 22) | (simple ? 0u : TL_GEN);
         }
       }
       const uint32_t m = g.ballot(t);
       const int dst = K + __popc(m & g.lt());
-      if (t && dst < L.Kmax) tlist[dst] = val;
+      if (t && dst < L.Kmax) {
+        tl(dst) = val;
+        if (bA != S) atomicOr(&bmask(bA, dst >> 5), 1u << (dst & 31));
+        if (bB != S) atomicOr(&bmask(bB, dst >> 5), 1u << (dst & 31));
+      }
       K += __popc(m);
     }
     if (K > L.Kmax) {
       if (g.lane == 0) hdr(H_STATUS) |= KB_STATUS_SOLVER_OVERFLOW;
       K = L.Kmax;
     }
-    for (int b = g.lane; b <= B; b += LPE) isl(b) = -1;
-    g.sync();
-    // ---- island DFS (b2World::Solve).  bodies flagged in (flo, fhi); contacts flagged per lane.
-    uint32_t flo = 0u, fhi = 0u;  // island flags of bodies, replicated in every lane
-    uint32_t cflag = 0u;          // bit s: tlist entry (s * LPE + lane) already in an island
-    int nOrd = 0, nIslands = 0;
-    int32_t* stack = reinterpret_cast<int32_t*>(sm + L.sStack);
-    const int chunks = (K + LPE - 1) / LPE;
-    for (int seed = B - 1; seed >= 0; --seed) {
-      if (((seed < 32 ? flo >> seed : fhi >> (seed - 32)) & 1u) != 0u) continue;
-      if (!awake(seed)) continue;
-      int sp = 0;
-      if (g.lane == 0) stack[0] = seed;
-      sp = 1;
-      if (seed < 32) flo |= 1u << seed; else fhi |= 1u << (seed - 32);
-      g.sync();
-      while (sp > 0) {
-        const int b = stack[sp - 1];
-        --sp;
-        g.sync();
-        if (g.lane == 0) {
+    for (int l = g.lane; l <= K + 1; l += LPE) lvlTab(l) = 0u;
+    g.usync();
+    // ---- lane 0: island DFS (b2World::Solve) in Box2D's order, dependency level of every constraint,
+    //      rows, and the level-sorted schedule.  Slot S of bmask collects the contacts already in an island.
+    if (g.lane == 0) {
+      unsigned long long bflag = 0ull;
+      int nOrd = 0, nIslands = 0, maxL = 0;
+      int32_t* stack = reinterpret_cast<int32_t*>(sm + L.sStack);
+      for (int seed = B - 1; seed >= 0; --seed) {
+        if (((bflag >> seed) & 1ull) != 0ull) continue;
+        if (!awake(seed)) continue;
+        int sp = 0;
+        stack[sp++] = seed;
+        bflag |= 1ull << seed;
+        while (sp > 0) {
+          const int b = stack[--sp];
           isl(b) = nIslands;
           wake(b);
-        }
-        for (int s = 0; s < chunks; ++s) {
-          const int t = s * LPE + g.lane;
-          bool inv = false;
-          uint32_t tv = 0u;
-          int other = S;
-          if (t < K && ((cflag >> s) & 1u) == 0u) {
-            tv = tlist[t];
-            const int bA = (tv >> 16) & 0xFF, bB = tv >> 24;
-            inv = bA == b || bB == b;
-            other = bA == b ? bB : bA;
+          for (int w = 0; w < KW; ++w) {
+            uint32_t m = bmask(b, w) & ~bmask(S, w);
+            if (m == 0u) continue;
+            bmask(S, w) |= m;
+            while (m != 0u) {
+              const int t = (w << 5) + __ffs(m) - 1;
+              m &= m - 1u;
+              const uint32_t tv = tl(t);
+              const int bA = (tv >> 16) & 63, bB = (tv >> 22) & 63;
+              const int other = bA == b ? bB : bA;
+              const uint32_t l = max(lastLvl(bA), lastLvl(bB)) + 1u;
+              lastLvl(bA) = l;
+              lastLvl(bB) = l;
+              lastLvl(S) = 0u;
+              ord(nOrd++) = (uint32_t)t | (l << 8) | ((uint32_t)nIslands << 16);
+              lvlTab(l) += 1u;
+              maxL = max(maxL, (int)l);
+              if (other != S && ((bflag >> other) & 1ull) == 0ull) {
+                bflag |= 1ull << other;
+                stack[sp++] = other;
+              }
+            }
           }
-          const uint32_t m = g.ballot(inv);
-          if (m == 0u) continue;
-          if (inv) {
-            const int dst = nOrd + __popc(m & g.lt());
-            ordC(dst) = (tv & 0xFFFF) | ((uint32_t)nIslands << 16);
-            cflag |= 1u << s;
+        }
+        ++nIslands;
+      }
+      // levels -> packed (cursor | first entry << 8 | first row << 16)
+      int e0 = 0, row = 0;
+      for (int l = 1; l <= maxL; ++l) {
+        const int c = (int)lvlTab(l);
+        lvlTab(l) = (uint32_t)e0 | ((uint32_t)e0 << 8) | ((uint32_t)row << 16);
+        e0 += c;
+        row += (c + LPE - 1) / LPE;
+      }
+      // scatter in constraint order: entries of one level keep Box2D's order
+      int nGen = 0;
+      for (int p = 0; p < nOrd; ++p) {
+        const uint32_t o = ord(p);
+        const uint32_t tv = tl(o & 0xFFu);
+        const int l = (o >> 8) & 0xFF;
+        const uint32_t w = lvlTab(l);
+        lvlTab(l) = w + 1u;
+        const int e = w & 0xFF, first = (w >> 8) & 0xFF;
+        const int r = (int)(w >> 16) + (e - first) / LPE;
+        const bool gen = (tv & TL_GEN) != 0u;
+        ent(e) = ((tv >> 16) & 0xFFFu) | ((o >> 16) << 12) | (gen ? IT_GEN : 0u) | ((uint32_t)r << 24);
+        entC(e) = (uint16_t)(tv & 0xFFFFu);
+        if (gen) {
+          if (nGen >= L.Gmax) {
+            hdr(H_STATUS) |= KB_STATUS_SOLVER_OVERFLOW;
+            nGen = L.Gmax - 1;
           }
-          nOrd += __popc(m);
-          // push unflagged dynamic neighbours in list order, first occurrence only
-          const bool cand = inv && other != S && ((other < 32 ? flo >> other : fhi >> (other - 32)) & 1u) == 0u;
-          const uint32_t same = g.match(cand ? (uint32_t)other : (0x100u + (uint32_t)g.lane));
-          const bool first = cand && (__ffs(same) - 1) == g.lane;
-          const uint32_t pm = g.ballot(first);
-          if (first) stack[sp + __popc(pm & g.lt())] = other;
-          sp += __popc(pm);
-          const uint32_t addlo = g.red_or(first && other < 32 ? 1u << other : 0u);
-          const uint32_t addhi = g.red_or(first && other >= 32 ? 1u << (other - 32) : 0u);
-          flo |= addlo;
-          fhi |= addhi;
-          g.sync();
+          sm[L.sRec + 8 * e] = (uint32_t)nGen++;
         }
       }
-      ++nIslands;
+      misc(0) = (uint32_t)nOrd;
+      misc(1) = (uint32_t)row;
+      misc(2) = (uint32_t)nIslands;
+      misc(3) = (uint32_t)maxL;
     }
-    g.sync();
-    if (g.lane == 0) {
-      cnt[KB_CNT_ISLANDS] += (unsigned long long)nIslands;
-    }
-    // ---- classify ordered contacts (simple: 1 slot, general: 3 slots) and fetch body ids
-    for (int p = g.lane; p < nOrd; p += LPE) {
-      const int ci = ordC(p) & 0xFFFF;
-      const uint32_t pr = cpair(ci);
-      const int pa = pr & 0xFFFF, pb = pr >> 16;
-      const int bA = __ldg(&px[pa].body), bB = __ldg(&px[pb].body);
-      const int pc = (cinfo(ci) & CI_PC_MASK) >> CI_PC_SHIFT;
-      const float fr = __ldg(&px[pa].friction) * __ldg(&px[pb].friction);
-      const float re = b2max(__ldg(&px[pa].restitution), __ldg(&px[pb].restitution));
-      const bool simple = pc == 1 && fr == 0.0f && re == 0.0f && __ldg(&px[pb].type) == SHAPE_CIRCLE;
-      ordB(p) = (uint32_t)bA | ((uint32_t)bB << 8) | ((simple ? 1u : 3u) << 16) | ((uint32_t)pc << 24);
-    }
-    g.sync();
-    // ---- dependency levels + counting sort by level (serial, lane 0)
-    int numLevels = 0, nEntries = 0;
-    if (g.lane == 0) {
-      uint32_t* lastLvl = sm + L.sLastLvl;
-      uint32_t* lvl = sm + L.sLvl;  // level per order position
-      for (int b = 0; b <= B; ++b) lastLvl[b] = 0u;
-      int maxL = 0;
-      for (int p = 0; p < nOrd; ++p) {
-        const uint32_t ob = ordB(p);
-        const int bA = ob & 0xFF, bB = (ob >> 8) & 0xFF;
-        uint32_t l = 0u;
-        if (bA != S) l = lastLvl[bA];
-        if (bB != S) l = max(l, lastLvl[bB]);
-        l += 1u;
-        if (bA != S) lastLvl[bA] = l;
-        if (bB != S) lastLvl[bB] = l;
-        lvl[p] = l;
-        maxL = max(maxL, (int)l);
-      }
-      // count entries / slots per level (lvlOff doubles as histogram)
-      uint32_t* slotOff = sm + L.sLvlOff + L.Kmax + 2;
-      for (int l = 0; l <= maxL + 1; ++l) {
-        lvlOff(l) = 0u;
-        slotOff[l] = 0u;
-      }
-      for (int p = 0; p < nOrd; ++p) {
-        lvlOff(lvl[p] + 1) += 1u;
-        slotOff[lvl[p] + 1] += (ordB(p) >> 16) & 0xFF;
-      }
-      for (int l = 1; l <= maxL + 1; ++l) {
-        lvlOff(l) += lvlOff(l - 1);
-        slotOff[l] += slotOff[l - 1];
-      }
-      // lvlOff(l) = first entry of level l (levels are 1-based; lvlOff(maxL+1) = nOrd)
-      int dropped = 0;
-      for (int p = 0; p < nOrd; ++p) {
-        const uint32_t l = lvl[p];
-        const uint32_t size = (ordB(p) >> 16) & 0xFF;
-        // cursors: lvlOff(l) and slotOff[l] are advanced in place and restored afterwards
-        const uint32_t e = lvlOff(l);
-        const uint32_t q = slotOff[l];
-        lvlOff(l) = e + 1u;
-        slotOff[l] = q + size;
-        if ((int)(q + size) > L.Kmax) {
-          entry(e) = 0xFFFFFFFFu;
-          ++dropped;
-        } else {
-          entry(e) = (uint32_t)p | (q << 16);
-        }
-      }
-      // restore offsets: after the pass lvlOff(l) == start of level l+1
-      for (int l = maxL + 1; l >= 1; --l) lvlOff(l) = lvlOff(l - 1);
-      lvlOff(0) = 0u;
-      if (dropped) hdr(H_STATUS) |= KB_STATUS_SOLVER_OVERFLOW;
-      misc(0) = (uint32_t)maxL;
-      cnt[KB_CNT_LEVELS] += (unsigned long long)maxL;
-    }
-    g.sync();
-    numLevels = (int)misc(0);
-    nEntries = nOrd;
+    g.usync();
+    const int nOrd = (int)misc(0), nRows = (int)misc(1), nIslands = (int)misc(2);
+    const int nRowsU = g.umax(nRows);  // warp-uniform row count: the groups of a warp sweep their rows in lock step
+    nIsl += (uint32_t)nIslands;
+    nLvl += misc(3);
     // ---- b2Island::Solve: integrate velocities (damping), remember the sweep start
     const float h = L.dt;
     for (int b = g.lane; b < B; b += LPE) {
@@ -1210,7 +1349,7 @@ struct Sim {
       const float4 p = pos4(b);
       const float4 x = xf4(b);
       sweep4(b) = make_float4(p.x, p.y, p.z, 0.0f);
-      reinterpret_cast<float2*>(sm + L.sSweep + 4 * (L.B + 1))[b] = make_float2(x.z, x.w);
+      oldq(b) = make_float2(x.z, x.w);
       float4 v = vel4(b);
       // (SimplePhototaxisKilobot's linearDamping = 0, lib/kilobot.py:203, is folded into the template)
       const float ld = __ldg(&bc[b].linearDamping);
@@ -1230,37 +1369,55 @@ struct Sim {
       }
       vel4(b) = v;
     }
-    g.sync();
-    // ---- constraints
-    for (int e = g.lane; e < nEntries; e += LPE)
-      if (entry(e) != 0xFFFFFFFFu) initConstraint(e);
-    g.sync();
-    unsigned long long pts = 0ull;
-    for (int e = g.lane; e < nEntries; e += LPE)
-      if (entry(e) != 0xFFFFFFFFu) pts += (ordB(entry(e) & 0xFFFF) >> 24) & 0xF;
-    pts = (unsigned long long)g.red_add((uint32_t)pts);
-    if (g.lane == 0) cnt[KB_CNT_POINTS] += pts;
-    // warm start (ordered)
-    for (int l = 1; l <= numLevels; ++l) {
-      const int e0 = (int)lvlOff(l), e1 = (int)lvlOff(l + 1);
-      for (int eb = e0; eb < e1; eb += LPE) {
-        const int e = eb + g.lane;
-        if (e < e1 && entry(e) != 0xFFFFFFFFu) warmStartOne(entry(e) >> 16);
+    g.usync();
+    // ---- constraints.  Entry e is owned by lane e % LPE for the whole solve.
+    {
+      uint32_t pts = 0u;
+      for (int e = g.lane; e < nOrd; e += LPE) {
+        const uint32_t item = ent(e);
+        const int ci = (int)entC(e);
+        if ((item & IT_GEN) != 0u) {
+          initGeneral(genSlot(e), ci, IT_BA(item), IT_BB(item), (uint32_t)ci | ((uint32_t)IT_ISL(item) << 16), false);
+          pts += (cw(ci) & CI_PC_MASK) >> CI_PC_SHIFT;
+        } else {
+          initSimple(e, ci, item);
+          pts += 1u;
+        }
       }
-      g.sync();
+      nPts += g.red_add(pts);
+    }
+    g.usync();
+    // warm start, then velocity iterations: a lane walks its entries in row order
+    {
+      int k = g.lane;
+      uint32_t item = k < nOrd ? ent(k) : IT_NONE;
+      for (int r = 0; r < nRowsU; ++r) {
+        if (IT_ROW(item) == r) {
+          if ((item & IT_GEN) != 0u) warmStartGeneral(genSlot(k));
+          else warmStartSimple(k, item);
+          k += LPE;
+          item = k < nOrd ? ent(k) : IT_NONE;
+        }
+        g.usync();
+      }
     }
     for (int it = 0; it < L.velIters; ++it) {
-      for (int l = 1; l <= numLevels; ++l) {
-        const int e0 = (int)lvlOff(l), e1 = (int)lvlOff(l + 1);
-        for (int eb = e0; eb < e1; eb += LPE) {
-          const int e = eb + g.lane;
-          if (e < e1 && entry(e) != 0xFFFFFFFFu) solveVelocityOne(entry(e) >> 16);
+      int k = g.lane;
+      uint32_t item = k < nOrd ? ent(k) : IT_NONE;
+      for (int r = 0; r < nRowsU; ++r) {
+        if (IT_ROW(item) == r) {
+          if ((item & IT_GEN) != 0u) solveVelocityGeneral(genSlot(k));
+          else solveVelocitySimple(k, item);
+          k += LPE;
+          item = k < nOrd ? ent(k) : IT_NONE;
         }
-        g.sync();
+        g.usync();
       }
     }
-    for (int e = g.lane; e < nEntries; e += LPE)
-      if (entry(e) != 0xFFFFFFFFu) storeImpulsesAndPreparePosition(e);
+    for (int e = g.lane; e < nOrd; e += LPE) {
+      if ((ent(e) & IT_GEN) != 0u) storeGeneral(genSlot(e));
+      else storeSimple(e, (int)entC(e));
+    }
     // ---- integrate positions
     for (int b = g.lane; b < B; b += LPE) {
       if (isl(b) < 0) continue;
@@ -1284,26 +1441,28 @@ struct Sim {
       vel4(b) = v;
     }
     for (int i = g.lane; i < nIslands; i += LPE) islflag(i) = 0u;  // bit0: unsolved this iteration, bit1: solved
-    g.sync();
+    g.usync();
     // ---- position iterations with per-island early exit
     {
       int remaining = nIslands;
-      for (int it = 0; it < L.posIters && remaining > 0; ++it) {
-        if (g.lane == 0) cnt[KB_CNT_POS_ITERS] += (unsigned long long)remaining;
-        for (int l = 1; l <= numLevels; ++l) {
-          const int e0 = (int)lvlOff(l), e1 = (int)lvlOff(l + 1);
-          for (int eb = e0; eb < e1; eb += LPE) {
-            const int e = eb + g.lane;
-            if (e < e1 && entry(e) != 0xFFFFFFFFu) {
-              const int q = entry(e) >> 16;
-              const int island = poolu(PF_AUX, q) >> 16;
-              if ((islflag(island) & 2u) == 0u) {
-                const bool ok = solvePositionOne(q, KB_BAUMGARTE, -3.0f * KB_LINEAR_SLOP, -1, -1);
-                if (!ok) atomicOr(&islflag(island), 1u);
-              }
+      for (int it = 0; it < L.posIters; ++it) {
+        if (!g.uany(remaining > 0)) break;
+        nPit += (uint32_t)remaining;
+        int k = g.lane;
+        uint32_t item = k < nOrd ? ent(k) : IT_NONE;
+        for (int r = 0; r < nRowsU; ++r) {
+          if (IT_ROW(item) == r) {
+            const int island = IT_ISL(item);
+            if ((islflag(island) & 2u) == 0u) {
+              const bool ok = (item & IT_GEN) != 0u
+                                  ? solvePositionGeneral(genSlot(k), KB_BAUMGARTE, -3.0f * KB_LINEAR_SLOP, -1, -1)
+                                  : solvePositionSimple(k, item);
+              if (!ok) atomicOr(&islflag(island), 1u);
             }
+            k += LPE;
+            item = k < nOrd ? ent(k) : IT_NONE;
           }
-          g.sync();
+          g.usync();
         }
         int solvedNow = 0;
         for (int i = g.lane; i < nIslands; i += LPE) {
@@ -1318,7 +1477,7 @@ struct Sim {
           }
         }
         remaining -= (int)g.red_add((uint32_t)solvedNow);
-        g.sync();
+        g.usync();
       }
     }
     // ---- copy back: SynchronizeTransform; sleep bookkeeping
@@ -1358,8 +1517,10 @@ struct Sim {
       }
       g.sync();
     }
+    g.usync();
     synchronizeFixtures(false);
     findNewContacts();
+    g.usync();
   }
 
   // shape AABB of proxy p under transform xf (b2Shape::ComputeAABB)
@@ -1396,8 +1557,8 @@ struct Sim {
   __device__ void synchronizeFixtures(bool toiMode) {
     uint32_t mlo = 0u, mhi = 0u;
     for (int p = g.lane; p < L.P; p += LPE) {
-      const int b = __ldg(&px[p].body);
-      if (b == S || b < 0) continue;
+      const int b = pbody(p);
+      if (b == S) continue;
       if (isl(b) < 0) continue;
       const float4 sw = sweep4(b);
       const float4 k = bc4(b);
@@ -1405,7 +1566,7 @@ struct Sim {
       if (toiMode) {
         xf1.q = rot_set(sw.z);
       } else {
-        const float2 oq = reinterpret_cast<const float2*>(sm + L.sSweep + 4 * (L.B + 1))[b];
+        const float2 oq = oldq(b);
         xf1.q.s = oq.x;
         xf1.q.c = oq.y;
       }
@@ -1432,8 +1593,8 @@ struct Sim {
     mlo = g.red_or(mlo);
     mhi = g.red_or(mhi);
     if (g.lane == 0) {
-      sm[L.sMoved] |= mlo;
-      sm[L.sMoved + 1] |= mhi;
+      hdr(H_MOVED) |= mlo;
+      hdr(H_MOVED + 1) |= mhi;
     }
     g.sync();
   }
@@ -1441,26 +1602,23 @@ struct Sim {
   // b2BroadPhase::UpdatePairs + b2ContactManager::AddPair.  Pairs (i < j) with a moved member are
   // visited in (i, j) order == Box2D's sorted pair buffer, so creation order matches.
   __device__ void findNewContacts() {
-    const uint32_t mlo = sm[L.sMoved], mhi = sm[L.sMoved + 1];
+    const uint32_t mlo = hdr(H_MOVED), mhi = hdr(H_MOVED + 1);
     g.sync();
+    if ((mlo | mhi) == 0u) return;
     if (g.lane == 0) {
-      sm[L.sMoved] = 0u;
-      sm[L.sMoved + 1] = 0u;
-    }
-    if ((mlo | mhi) == 0u) {
-      g.sync();
-      return;
+      hdr(H_MOVED) = 0u;
+      hdr(H_MOVED + 1) = 0u;
     }
     const unsigned long long moved = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
     int nC = (int)hdr(H_NC);
     bool overflow = false;
-    unsigned long long tests = 0ull;
+    uint32_t tests = 0u;
     const int P = L.P;
     for (int i = 0; i < P - 1; ++i) {
       const bool movedI = ((moved >> i) & 1ull) != 0ull;
       if (!movedI && (moved >> (i + 1)) == 0ull) break;
       const float4 fi = fat4(i);
-      const int bi = __ldg(&px[i].body);
+      const int bi = pbody(i);
       const int ti = __ldg(&px[i].type);
       const unsigned long long adjI = (unsigned long long)adj(i, 0) | ((unsigned long long)adj(i, 1) << 32);
       for (int jb = i + 1; jb < P; jb += LPE) {
@@ -1471,8 +1629,7 @@ struct Sim {
           ++tests;
           const float4 fj = fat4(j);
           const bool overlap = !(fj.x - fi.z > 0.0f || fj.y - fi.w > 0.0f || fi.x - fj.z > 0.0f || fi.y - fj.w > 0.0f);
-          bj = __ldg(&px[j].body);
-          tj = __ldg(&px[j].type);
+          bj = pbody(j);
           create = overlap && bi != bj && ((adjI >> j) & 1ull) == 0ull;
         }
         const uint32_t m = g.ballot(create);
@@ -1481,11 +1638,11 @@ struct Sim {
         if (create) {
           if (dst < L.Cmax) {
             // type register: chain edge < polygon < circle takes the A slot (b2Contact::Create)
+            tj = __ldg(&px[j].type);
             const int rankI = ti == SHAPE_EDGE ? 0 : (ti == SHAPE_POLYGON ? 1 : 2);
             const int rankJ = tj == SHAPE_EDGE ? 0 : (tj == SHAPE_POLYGON ? 1 : 2);
             const int pa = rankI > rankJ ? j : i, pb = rankI > rankJ ? i : j;
-            cpair(dst) = (uint32_t)pa | ((uint32_t)pb << 16);
-            cinfo(dst) = CI_ENABLED;
+            cw(dst) = (uint32_t)pa | ((uint32_t)pb << 8) | CI_ENABLED;
             atomicOr(&adj(i, j >> 5), 1u << (j & 31));
             atomicOr(&adj(j, i >> 5), 1u << (i & 31));
             wake(bj);
@@ -1498,24 +1655,23 @@ struct Sim {
         g.sync();
       }
     }
-    tests = (unsigned long long)g.red_add((uint32_t)tests);
-    if (g.lane == 0) {
-      hdr(H_NC) = (uint32_t)nC;
-      counters()[KB_CNT_PAIR_TESTS] += tests;
-    }
+    nTests += g.red_add(tests);
+    if (g.lane == 0) hdr(H_NC) = (uint32_t)nC;
     if (g.any(overflow) && g.lane == 0) hdr(H_STATUS) |= KB_STATUS_CONTACT_OVERFLOW;
     g.sync();
   }
 
   // b2World::Step(dt, velIters, posIters)
   __device__ void worldStep() {
-    if (g.lane == 0) {
-      counters()[KB_CNT_SUBSTEPS] += 1ull;
-      counters()[KB_CNT_CONTACTS] += (unsigned long long)hdr(H_NC);
-    }
+    nSub += 1u;
+    nCon += hdr(H_NC);
     collide();
+    g.usync();
     solve();
-    if (L.enableToi) solveTOI();
+    if (L.enableToi) {
+      solveTOI();
+      g.usync();
+    }
   }
 
   __device__ void solveTOI();

@@ -428,19 +428,19 @@ __device__ __noinline__ bool time_of_impact(const ProxyConst* shapeA, SweepD swe
 }
 
 // ------------------------------------------------------------------------ b2World::SolveTOI
-template <int LPE>
-__device__ void Sim<LPE>::solveTOI() {
+template <int LPE, bool UNI>
+__device__ __noinline__ void Sim<LPE, UNI>::solveTOI() {
   const int B = L.B;
-  float* toi = reinterpret_cast<float*>(sm + L.sToi);  // cached alpha per contact
+  float* toi = toiCache();  // cached alpha per contact (HBM/L2; only touched when a table contact exists)
   int nC = (int)hdr(H_NC);
   // any contact with the table at all?  (the common case is none: skip everything)
   bool wallContact = false;
-  for (int i = g.lane; i < nC; i += LPE) wallContact |= __ldg(&px[cpair(i) & 0xFFFF].body) == S;
+  for (int i = g.lane; i < nC; i += LPE) wallContact |= pbody(CW_PA(cw(i))) == S;
   if (!g.any(wallContact)) return;
 
   for (int b = g.lane; b <= B; b += LPE) reinterpret_cast<float*>(&sweep4(b))[3] = 0.0f;  // alpha0 = 0
   for (int i = g.lane; i < nC; i += LPE) {
-    cinfo(i) &= ~(CI_TOI | CI_ISLAND | CI_TOICOUNT_MASK);
+    cw(i) &= ~(CI_TOI | CI_TOICOUNT_MASK);
     toi[i] = 1.0f;
   }
   g.sync();
@@ -455,14 +455,13 @@ __device__ void Sim<LPE>::solveTOI() {
       bool need = false;
       int pa = 0, pb = 0, bd = S;
       if (i < nC) {
-        const uint32_t info = cinfo(i);
-        const bool enabled = (info & CI_ENABLED) != 0u;
-        const int toiCount = (info & CI_TOICOUNT_MASK) >> CI_TOICOUNT_SHIFT;
-        if (enabled && toiCount <= KB_MAX_SUB_STEPS && (info & CI_TOI) == 0u) {
-          const uint32_t pr = cpair(i);
-          pa = pr & 0xFFFF;
-          pb = pr >> 16;
-          const int bA = __ldg(&px[pa].body), bB = __ldg(&px[pb].body);
+        const uint32_t w = cw(i);
+        const bool enabled = (w & CI_ENABLED) != 0u;
+        const int toiCount = (w & CI_TOICOUNT_MASK) >> CI_TOICOUNT_SHIFT;
+        if (enabled && toiCount <= KB_MAX_SUB_STEPS && (w & CI_TOI) == 0u) {
+          pa = CW_PA(w);
+          pb = CW_PB(w);
+          const int bA = pbody(pa), bB = pbody(pb);
           // chain is always fixture A, so the table can only be body A
           if (bA == S && bB != S && awake(bB)) {
             need = true;
@@ -498,7 +497,7 @@ __device__ void Sim<LPE>::solveTOI() {
         float alpha = 1.0f;
         if (time_of_impact(px + pa, sA, px + pb, sB, &beta)) alpha = b2min(alpha0 + (1.0f - alpha0) * beta, 1.0f);
         toi[i] = alpha;
-        cinfo(i) |= CI_TOI;
+        cw(i) |= CI_TOI;
       }
       g.sync();
     }
@@ -508,9 +507,9 @@ __device__ void Sim<LPE>::solveTOI() {
     for (int base = 0; base < nC; base += LPE) {
       const int i = base + g.lane;
       if (i < nC) {
-        const uint32_t info = cinfo(i);
-        const int toiCount = (info & CI_TOICOUNT_MASK) >> CI_TOICOUNT_SHIFT;
-        if ((info & CI_ENABLED) != 0u && toiCount <= KB_MAX_SUB_STEPS && (info & CI_TOI) != 0u) {
+        const uint32_t w = cw(i);
+        const int toiCount = (w & CI_TOICOUNT_MASK) >> CI_TOICOUNT_SHIFT;
+        if ((w & CI_ENABLED) != 0u && toiCount <= KB_MAX_SUB_STEPS && (w & CI_TOI) != 0u) {
           const float alpha = toi[i];
           if (alpha < 1.0f) {
             const uint32_t bits = f2u(alpha);
@@ -528,9 +527,8 @@ __device__ void Sim<LPE>::solveTOI() {
     const float minAlpha = u2f(minBits);
     if (minContact < 0 || 1.0f - 10.0f * KB_EPS < minAlpha) break;
 
-    if (g.lane == 0) counters()[KB_CNT_TOI_EVENTS] += 1ull;
-    const uint32_t mpr = cpair(minContact);
-    const int bd = __ldg(&px[mpr >> 16].body);  // the dynamic body (fixture B)
+    nToi += 1u;
+    const int bd = pbody(CW_PB(cw(minContact)));  // the dynamic body (fixture B)
     // backups, advance both bodies to minAlpha (b2Body::Advance)
     const float4 backupSweep = sweep4(bd), backupPos = pos4(bd), backupXf = xf4(bd);
     const float4 backupTable = sweep4(S);
@@ -553,16 +551,17 @@ __device__ void Sim<LPE>::solveTOI() {
       reinterpret_cast<float*>(&sweep4(S))[3] = minAlpha;
       // minContact->Update()
       updateContact(minContact);
-      uint32_t info = cinfo(minContact);
-      info &= ~CI_TOI;
-      const uint32_t tc = ((info & CI_TOICOUNT_MASK) >> CI_TOICOUNT_SHIFT) + 1u;
-      info = (info & ~CI_TOICOUNT_MASK) | (tc << CI_TOICOUNT_SHIFT);
-      cinfo(minContact) = info;
+      uint32_t w = cw(minContact);
+      w &= ~CI_TOI;
+      const uint32_t tc = ((w & CI_TOICOUNT_MASK) >> CI_TOICOUNT_SHIFT) + 1u;
+      w = (w & ~CI_TOICOUNT_MASK) | (tc << CI_TOICOUNT_SHIFT);
+      cw(minContact) = w;
     }
     g.sync();
-    if ((cinfo(minContact) & CI_TOUCHING) == 0u) {
+    if ((cw(minContact) & CI_TOUCHING) == 0u) {
+      g.sync();
       if (g.lane == 0) {
-        cinfo(minContact) &= ~CI_ENABLED;
+        cw(minContact) &= ~CI_ENABLED;
         sweep4(bd) = backupSweep;
         // restoring m_sweep leaves c/a at the backup values; SynchronizeTransform
         pos4(bd) = backupPos;
@@ -576,62 +575,40 @@ __device__ void Sim<LPE>::solveTOI() {
     g.sync();
     // ---- mini island: minContact first, then the body's other touching wall contacts in list order
     //      (each re-evaluated at the advanced pose)
+    const int islandCap = min(KB_MAX_TOI_CONTACTS, min(L.Gmax, L.Kmax));
     int nIsland = 1;
-    if (g.lane == 0) ordC(0) = (uint32_t)minContact;
+    if (g.lane == 0) ord(0) = (uint32_t)minContact;
     for (int base = 0; base < nC; base += LPE) {
       const int i = nC - 1 - (base + g.lane);
       bool add = false;
       if (i >= 0 && i != minContact) {
-        const uint32_t pr = cpair(i);
-        const int bA = __ldg(&px[pr & 0xFFFF].body), bB = __ldg(&px[pr >> 16].body);
-        if (bA == S && bB == bd) {
+        const uint32_t w = cw(i);
+        if (pbody(CW_PA(w)) == S && pbody(CW_PB(w)) == bd) {
           updateContact(i);
-          add = (cinfo(i) & (CI_ENABLED | CI_TOUCHING)) == (CI_ENABLED | CI_TOUCHING);
+          add = (cw(i) & (CI_ENABLED | CI_TOUCHING)) == (CI_ENABLED | CI_TOUCHING);
         }
       }
       const uint32_t m = g.ballot(add);
       const int dst = nIsland + __popc(m & g.lt());
-      if (add && dst < KB_MAX_TOI_CONTACTS && 3 * dst + 3 <= L.Kmax) ordC(dst) = (uint32_t)i;
-      nIsland = min(nIsland + __popc(m), min(KB_MAX_TOI_CONTACTS, L.Kmax / 3));
+      if (add && dst < islandCap) ord(dst) = (uint32_t)i;
+      nIsland = min(nIsland + __popc(m), islandCap);
     }
     g.sync();
-    // ---- b2Island::SolveTOI (one dynamic body: strictly sequential, lane 0)
+    // ---- b2Island::SolveTOI (one dynamic body: strictly sequential, lane 0; general-constraint records)
     if (g.lane == 0) {
       const float subDt = (1.0f - minAlpha) * L.dt;
+      // position constraints first: load manifold data into the records (position layout)
       for (int k = 0; k < nIsland; ++k) {
-        const int ci = ordC(k) & 0xFFFF;
-        const uint32_t pr = cpair(ci);
-        const int pc = (cinfo(ci) & CI_PC_MASK) >> CI_PC_SHIFT;
-        ordB(k) = (uint32_t)S | ((uint32_t)bd << 8) | (3u << 16) | ((uint32_t)pc << 24);
-        (void)pr;
-        entry(k) = (uint32_t)k | ((uint32_t)(3 * k) << 16);
-      }
-      // position constraints first: load manifold data into the pool (position layout)
-      for (int k = 0; k < nIsland; ++k) {
-        const int q = 3 * k;
-        const int ci = ordC(k) & 0xFFFF;
-        const float4* rec = reinterpret_cast<const float4*>(manifoldRec(ci));
-        const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
-        const uint32_t tp = f2u(r3.z);
-        const int type = tp & 0xFF, pointCount = (tp >> 8) & 0xFF;
-        const uint32_t pr = cpair(ci);
-        poolu(PF_IDX, q) = (uint32_t)S | ((uint32_t)bd << 8) | ((uint32_t)pointCount << 16) | (1u << 20) |
-                           ((uint32_t)type << 24) | ((uint32_t)pointCount << 28);
-        poolu(PF_AUX, q) = (uint32_t)ci;
-        pool(PF_NX, q) = r0.x;
-        pool(PF_NY, q) = r0.y;
-        pool(PF_RAX, q) = r0.z;
-        pool(PF_RAY, q) = r0.w;
-        pool(PF_RBX, q) = __ldg(&px[pr & 0xFFFF].radius);
-        pool(PF_RBY, q) = __ldg(&px[pr >> 16].radius);
-        gw(q, 10) = r1.x;
-        gw(q, 11) = r1.y;
-        gw(q, 12) = r2.y;
-        gw(q, 13) = r2.z;
+        const int ci = (int)ord(k);
+        const uint32_t tp = f2u(manifoldRec(ci)[MR_TYPE]);
+        const uint32_t type = tp & 0xFF, pointCount = (tp >> 8) & 0xFF;
+        poolu(PF_IDX, k) = (uint32_t)S | ((uint32_t)bd << 8) | (pointCount << 16) | (type << 24) | (pointCount << 28);
+        poolu(PF_AUX, k) = (uint32_t)ci;
+        preparePositionGeneral(k, ci);
       }
       for (int it = 0; it < 20; ++it) {
         bool ok = true;
-        for (int k = 0; k < nIsland; ++k) ok &= solvePositionOne(3 * k, KB_TOI_BAUMGARTE, -1.5f * KB_LINEAR_SLOP, S, bd);
+        for (int k = 0; k < nIsland; ++k) ok &= solvePositionGeneral(k, KB_TOI_BAUMGARTE, -1.5f * KB_LINEAR_SLOP, S, bd);
         if (ok) break;
       }
       {
@@ -640,9 +617,9 @@ __device__ void Sim<LPE>::solveTOI() {
         sw[0] = p.x; sw[1] = p.y; sw[2] = p.z;  // c0, a0 = corrected pose
       }
       // velocity constraints without warm starting, at the corrected pose
-      for (int k = 0; k < nIsland; ++k) initConstraint(k, true);
+      for (int k = 0; k < nIsland; ++k) initGeneral(k, (int)ord(k), S, bd, ord(k), true);
       for (int it = 0; it < L.velIters; ++it)
-        for (int k = 0; k < nIsland; ++k) solveVelocityOne(3 * k);
+        for (int k = 0; k < nIsland; ++k) solveVelocityGeneral(k);
       // integrate the remainder of the step
       {
         const float h = subDt;
@@ -675,8 +652,8 @@ __device__ void Sim<LPE>::solveTOI() {
     synchronizeFixtures(true);
     // invalidate the cached TOIs of every contact of the displaced body
     for (int i = g.lane; i < nC; i += LPE) {
-      const uint32_t pr = cpair(i);
-      if (__ldg(&px[pr & 0xFFFF].body) == bd || __ldg(&px[pr >> 16].body) == bd) cinfo(i) &= ~(CI_TOI | CI_ISLAND);
+      const uint32_t w = cw(i);
+      if (pbody(CW_PA(w)) == bd || pbody(CW_PB(w)) == bd) cw(i) = w & ~CI_TOI;
     }
     g.sync();
     const int before = (int)hdr(H_NC);
