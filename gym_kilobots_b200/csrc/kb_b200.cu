@@ -29,14 +29,13 @@ namespace kb {
 // last real env and never write outputs.
 template <int LPE>
 __global__ void __launch_bounds__(KB_BLOCK) kb_step_kernel(const __grid_constant__ KernelArgs a) {
-  extern __shared__ __align__(16) uint32_t smem[];
   constexpr int EPB = KB_BLOCK / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
   const int envIn = min(env, a.numEnvs - 1);
   Sim<LPE, true> s(a.L);
   s.g.init();
-  s.sm = smem + (size_t)slot * a.L.smemWords;
+  s.sb = (uint32_t)slot * (uint32_t)a.L.smemWords;
   s.blob = a.blobs + (size_t)env * a.L.blobWords;
   const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * a.L.Pp;
@@ -61,7 +60,6 @@ __global__ void __launch_bounds__(KB_BLOCK) kb_step_kernel(const __grid_constant
 
 template <int LPE>
 __global__ void __launch_bounds__(KB_BLOCK) kb_reset_kernel(const __grid_constant__ KernelArgs a) {
-  extern __shared__ __align__(16) uint32_t smem[];
   constexpr int EPB = KB_BLOCK / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
@@ -70,7 +68,7 @@ __global__ void __launch_bounds__(KB_BLOCK) kb_reset_kernel(const __grid_constan
   const Layout& L = a.L;
   Sim<LPE, false> s(a.L);
   s.g.init();
-  s.sm = smem + (size_t)slot * L.smemWords;
+  s.sb = (uint32_t)slot * (uint32_t)L.smemWords;
   s.blob = a.blobs + (size_t)env * L.blobWords;
   const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * L.Pp;
@@ -78,7 +76,7 @@ __global__ void __launch_bounds__(KB_BLOCK) kb_reset_kernel(const __grid_constan
   s.lights = a.lights;
   s.S = L.B;
   const int lane = s.g.lane;
-  for (int i = lane; i < L.stateWords; i += LPE) s.sm[i] = 0u;
+  for (int i = lane; i < L.stateWords; i += LPE) s.smp()[i] = 0u;
   for (int i = lane; i < 2 * KB_NUM_COUNTERS; i += LPE) reinterpret_cast<uint32_t*>(s.blob)[L.oCnt + i] = 0u;
   s.g.sync();
   if (lane == 0) {
@@ -149,7 +147,6 @@ __global__ void __launch_bounds__(KB_BLOCK) kb_reset_kernel(const __grid_constan
 // Body.set_pose (lib/body.py:67-69) -> b2Body::SetTransform
 template <int LPE>
 __global__ void __launch_bounds__(KB_BLOCK) kb_setpose_kernel(const __grid_constant__ KernelArgs a) {
-  extern __shared__ __align__(16) uint32_t smem[];
   constexpr int EPB = KB_BLOCK / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
@@ -157,7 +154,7 @@ __global__ void __launch_bounds__(KB_BLOCK) kb_setpose_kernel(const __grid_const
   const Layout& L = a.L;
   Sim<LPE, false> s(a.L);
   s.g.init();
-  s.sm = smem + (size_t)slot * L.smemWords;
+  s.sb = (uint32_t)slot * (uint32_t)L.smemWords;
   s.blob = a.blobs + (size_t)env * L.blobWords;
   const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * L.Pp;

@@ -68,11 +68,26 @@ struct KernelArgs {
 #define IT_ROW(x) ((int)((x) >> 24))
 #define IT_NONE 0xFFFFFFFFu
 
+// All shared-memory accesses index this symbol so that the compiler emits LDS/STS with 32-bit
+// addresses (a pointer kept in a struct decays to generic LD/ST).
+extern __shared__ __align__(16) uint32_t kb_smem[];
+
+template <int LPE, bool UNI>
+struct Sim;
+// out-of-line (cold) paths: the Sim travels BY VALUE so that the caller's copy stays in registers
+template <int LPE, bool UNI> __device__ __noinline__ void warmStartGeneralNI(Sim<LPE, UNI> s, int q);
+template <int LPE, bool UNI> __device__ __noinline__ void solveVelocityGeneralNI(Sim<LPE, UNI> s, int q);
+template <int LPE, bool UNI> __device__ __noinline__ bool solvePositionGeneralNI(Sim<LPE, UNI> s, int q);
+template <int LPE, bool UNI> __device__ __noinline__ void initGeneralNI(Sim<LPE, UNI> s, int q, int ci, uint32_t item);
+template <int LPE, bool UNI> __device__ __noinline__ void storeGeneralNI(Sim<LPE, UNI> s, int q);
+template <int LPE, bool UNI> __device__ __noinline__ uint32_t solveTOINI(Sim<LPE, UNI> s);
+
 template <int LPE, bool UNI>
 struct Sim {
   Group<LPE, UNI> g;
   const Layout& L;
-  uint32_t* sm;                 // this env's shared memory (words)
+  uint32_t sb;                  // word offset of this env's shared-memory region in kb_smem
+  __device__ __forceinline__ uint32_t* smp() const { return kb_smem + sb; }
   float* blob;                  // this env's state blob in HBM
   const ProxyConst* px;         // scene proxies
   const BodyConst* bc;          // scene bodies
@@ -86,29 +101,29 @@ struct Sim {
   }
 
   // ---- typed views into shared memory
-  __device__ __forceinline__ float4& pos4(int b) { return reinterpret_cast<float4*>(sm + L.oPos)[b]; }   // cx cy a sleepTime
-  __device__ __forceinline__ float4& vel4(int b) { return reinterpret_cast<float4*>(sm + L.oVel)[b]; }   // vx vy w flags
-  __device__ __forceinline__ float4& xf4(int b) { return reinterpret_cast<float4*>(sm + L.oXf)[b]; }     // px py qs qc
-  __device__ __forceinline__ float4& fat4(int p) { return reinterpret_cast<float4*>(sm + L.oFat)[p]; }   // lx ly ux uy
-  __device__ __forceinline__ float4& sweep4(int b) { return reinterpret_cast<float4*>(sm + L.sSweep)[b]; } // c0x c0y a0 alpha0
-  __device__ __forceinline__ float2& oldq(int b) { return reinterpret_cast<float2*>(sm + L.sOldQ)[b]; }  // xf.q at step start
-  __device__ __forceinline__ float4& bc4(int b) { return reinterpret_cast<float4*>(sm + L.sBc)[b]; }     // invMass invI lcx lcy
-  __device__ __forceinline__ float4& rec4(int i) { return reinterpret_cast<float4*>(sm + L.sRec)[i]; }   // 2 per schedule entry
-  __device__ __forceinline__ uint32_t& cw(int i) { return sm[L.oCw + i]; }
-  __device__ __forceinline__ uint32_t& hdr(int i) { return sm[L.oHdr + i]; }
-  __device__ __forceinline__ int32_t& isl(int b) { return reinterpret_cast<int32_t*>(sm + L.sIsl)[b]; }
-  __device__ __forceinline__ uint32_t& islflag(int i) { return sm[L.sIslFlag + i]; }
-  __device__ __forceinline__ uint32_t& misc(int i) { return sm[L.sMisc + i]; }
-  __device__ __forceinline__ uint32_t& adj(int p, int hi) { return sm[L.sAdj + 2 * p + hi]; }
-  __device__ __forceinline__ uint32_t& bmask(int b, int w) { return sm[L.sBmask + b * L.KW + w]; }
-  __device__ __forceinline__ uint32_t& tl(int t) { return sm[L.sTl + t]; }
-  __device__ __forceinline__ uint32_t& ord(int p) { return sm[L.sOrd + p]; }
-  __device__ __forceinline__ uint32_t& ent(int e) { return sm[L.sEnt + e]; }
-  __device__ __forceinline__ uint16_t& entC(int e) { return reinterpret_cast<uint16_t*>(sm + L.sEntC)[e]; }
-  __device__ __forceinline__ uint32_t& lvlTab(int l) { return sm[L.sLvlTab + l]; }
-  __device__ __forceinline__ uint32_t& lastLvl(int b) { return sm[L.sLastLvl + b]; }
-  __device__ __forceinline__ int pbody(int p) { return (int)reinterpret_cast<const uint8_t*>(sm + L.sPb)[p]; }
-  __device__ __forceinline__ double* lightState() { return reinterpret_cast<double*>(sm + L.oLight); }
+  __device__ __forceinline__ float4& pos4(int b) { return reinterpret_cast<float4*>(smp() + L.oPos)[b]; }   // cx cy a sleepTime
+  __device__ __forceinline__ float4& vel4(int b) { return reinterpret_cast<float4*>(smp() + L.oVel)[b]; }   // vx vy w flags
+  __device__ __forceinline__ float4& xf4(int b) { return reinterpret_cast<float4*>(smp() + L.oXf)[b]; }     // px py qs qc
+  __device__ __forceinline__ float4& fat4(int p) { return reinterpret_cast<float4*>(smp() + L.oFat)[p]; }   // lx ly ux uy
+  __device__ __forceinline__ float4& sweep4(int b) { return reinterpret_cast<float4*>(smp() + L.sSweep)[b]; } // c0x c0y a0 alpha0
+  __device__ __forceinline__ float2& oldq(int b) { return reinterpret_cast<float2*>(smp() + L.sOldQ)[b]; }  // xf.q at step start
+  __device__ __forceinline__ float4& bc4(int b) { return reinterpret_cast<float4*>(smp() + L.sBc)[b]; }     // invMass invI lcx lcy
+  __device__ __forceinline__ float4& rec4(int i) { return reinterpret_cast<float4*>(smp() + L.sRec)[i]; }   // 2 per schedule entry
+  __device__ __forceinline__ uint32_t& cw(int i) { return smp()[L.oCw + i]; }
+  __device__ __forceinline__ uint32_t& hdr(int i) { return smp()[L.oHdr + i]; }
+  __device__ __forceinline__ int32_t& isl(int b) { return reinterpret_cast<int32_t*>(smp() + L.sIsl)[b]; }
+  __device__ __forceinline__ uint32_t& islflag(int i) { return smp()[L.sIslFlag + i]; }
+  __device__ __forceinline__ uint32_t& misc(int i) { return smp()[L.sMisc + i]; }
+  __device__ __forceinline__ uint32_t& adj(int p, int hi) { return smp()[L.sAdj + 2 * p + hi]; }
+  __device__ __forceinline__ uint32_t& bmask(int b, int w) { return smp()[L.sBmask + b * L.KW + w]; }
+  __device__ __forceinline__ uint32_t& tl(int t) { return smp()[L.sTl + t]; }
+  __device__ __forceinline__ uint32_t& ord(int p) { return smp()[L.sOrd + p]; }
+  __device__ __forceinline__ uint32_t& ent(int e) { return smp()[L.sEnt + e]; }
+  __device__ __forceinline__ uint16_t& entC(int e) { return reinterpret_cast<uint16_t*>(smp() + L.sEntC)[e]; }
+  __device__ __forceinline__ uint32_t& lvlTab(int l) { return smp()[L.sLvlTab + l]; }
+  __device__ __forceinline__ uint32_t& lastLvl(int b) { return smp()[L.sLastLvl + b]; }
+  __device__ __forceinline__ int pbody(int p) { return (int)reinterpret_cast<const uint8_t*>(smp() + L.sPb)[p]; }
+  __device__ __forceinline__ double* lightState() { return reinterpret_cast<double*>(smp() + L.oLight); }
   // ---- HBM/L2-resident parts of the blob
   __device__ __forceinline__ double* ctrl(int k) { return reinterpret_cast<double*>(blob + L.oCtrl) + 4 * k; }
   __device__ __forceinline__ float* manifoldRec(int i) { return blob + L.oMan + MR_WORDS * i; }
@@ -137,17 +152,17 @@ struct Sim {
   }
 
   // ------------------------------------------------------------------------- state I/O
-  __device__ void loadState() {
+  __device__ __forceinline__ void loadState() {
     const float4* src = reinterpret_cast<const float4*>(blob);
-    float4* dst = reinterpret_cast<float4*>(sm);
+    float4* dst = reinterpret_cast<float4*>(smp());
     const int n4 = L.stateWords >> 2;
     for (int i = g.lane; i < n4; i += LPE) dst[i] = src[i];
     g.sync();
   }
-  __device__ void storeState() {
+  __device__ __forceinline__ void storeState() {
     g.sync();
     float4* dst = reinterpret_cast<float4*>(blob);
-    const float4* src = reinterpret_cast<const float4*>(sm);
+    const float4* src = reinterpret_cast<const float4*>(smp());
     const int n4 = L.stateWords >> 2;
     for (int i = g.lane; i < n4; i += LPE) dst[i] = src[i];
     if (g.lane == 0) {
@@ -164,7 +179,7 @@ struct Sim {
   }
   // scratch that is constant for the launch: body constants, static-table slot, proxy->body map,
   // adjacency masks of the persistent contact list
-  __device__ void initScratch() {
+  __device__ __forceinline__ void initScratch() {
     for (int b = g.lane; b <= L.B; b += LPE) {
       if (b < L.B) {
         const BodyConst* c = bc + b;
@@ -177,8 +192,8 @@ struct Sim {
         sweep4(b) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
     }
-    for (int p = g.lane; p < L.P; p += LPE) reinterpret_cast<uint8_t*>(sm + L.sPb)[p] = (uint8_t)__ldg(&px[p].body);
-    for (int p = g.lane; p < 2 * L.P; p += LPE) sm[L.sAdj + p] = 0u;
+    for (int p = g.lane; p < L.P; p += LPE) reinterpret_cast<uint8_t*>(smp() + L.sPb)[p] = (uint8_t)__ldg(&px[p].body);
+    for (int p = g.lane; p < 2 * L.P; p += LPE) smp()[L.sAdj + p] = 0u;
     g.sync();
     const int nC = (int)hdr(H_NC);
     for (int i = g.lane; i < nC; i += LPE) {
@@ -195,7 +210,7 @@ struct Sim {
     double m = a > lo ? a : lo;
     return m < hi ? m : hi;
   }
-  __device__ void lightStep(const double* action) {
+  __device__ __forceinline__ void lightStep(const double* action) {
     if (g.lane == 0) {
       double* ls = lightState();
       int so = 0, ao = 0;
@@ -251,8 +266,8 @@ struct Sim {
   __device__ __forceinline__ void lightValueGrad(const LightConst& lc, const double* ls, double sx, double sy,
                                                  double* value, double* gx, double* gy) {
     if (lc.type == KB_LIGHT_LINEAR) {
-      double vx, vy;
-      kb_sincosd(ls[0], &vy, &vx);
+      const double2 sc = kb_sincosd(ls[0]);
+      const double vx = sc.y, vy = sc.x;
       *value = vx * sx + vy * sy;
       *gx = vx;
       *gy = vy;
@@ -294,7 +309,7 @@ struct Sim {
     reinterpret_cast<float*>(&vel4(b))[2] = w;
   }
 
-  __device__ void setKilobotActions(const double* action) {
+  __device__ __forceinline__ void setKilobotActions(const double* action) {
     const double hpi = 0.5 * 3.141592653589793;
     const double pi = 3.141592653589793;
     for (int k = g.lane; k < L.N; k += LPE) {
@@ -322,7 +337,7 @@ struct Sim {
     g.sync();
   }
 
-  __device__ void senseControl() {
+  __device__ __forceinline__ void senseControl() {
     const double* ls = lightState();
     for (int k = g.lane; k < L.N; k += LPE) {
       const int b = L.M + k;
@@ -414,8 +429,8 @@ struct Sim {
         }  // fallthrough
         case KB_KILOBOT_VELOCITY: {
           double ang = (double)pos4(b).z;
-          double lx, ly;
-          kb_sincosd(ang, &ly, &lx);
+          const double2 sc = kb_sincosd(ang);
+          double lx = sc.y, ly = sc.x;
           lx *= c[0] * 25.0;
           ly *= c[0] * 25.0;
           setLinearVelocity(b, mk((float)lx, (float)ly));
@@ -496,14 +511,14 @@ struct Sim {
 
   // b2ContactManager::Collide.  World-list order is descending array index; a sleeping pair is
   // only visited if an earlier (higher index) contact woke one of its bodies.
-  __device__ void collide() {
+  __device__ __forceinline__ void collide() {
     const int nC = (int)hdr(H_NC);
     if (nC == 0) return;
     // any sleeping dynamic body?
     bool sleepy = false;
     for (int b = g.lane; b < L.B; b += LPE) sleepy |= !awake(b);
     const bool anyAsleep = g.any(sleepy);
-    int32_t* wakeAt = reinterpret_cast<int32_t*>(sm + L.sStack);  // reuse: per body, highest waking contact index
+    int32_t* wakeAt = reinterpret_cast<int32_t*>(smp() + L.sStack);  // reuse: per body, highest waking contact index
     if (anyAsleep) {
       for (int b = g.lane; b <= L.B; b += LPE) wakeAt[b] = awake(b) ? 0x7FFFFFFF : -1;
       g.sync();
@@ -798,7 +813,7 @@ struct Sim {
   // one lane owns a record for the whole solve, so no cross-lane visibility is needed.
   // b2ContactSolver ctor + InitializeVelocityConstraints for general slot q.  fresh == true is the
   // TOI island variant: rotations rebuilt from the (corrected) angles, no warm starting.
-  __device__ __noinline__ void initGeneral(int q, int ci, int bA, int bB, uint32_t aux, bool fresh) {
+  __device__ __forceinline__ void initGeneral(int q, int ci, int bA, int bB, uint32_t aux, bool fresh) {
     const uint32_t w = cw(ci);
     const int pa = CW_PA(w), pb = CW_PB(w);
     const float4* rec = reinterpret_cast<const float4*>(manifoldRec(ci));
@@ -956,7 +971,7 @@ struct Sim {
   }
 
   // b2ContactSolver::WarmStart for one general constraint
-  __device__ __noinline__ void warmStartGeneral(int q) {
+  __device__ __forceinline__ void warmStartGeneral(int q) {
     const uint32_t idx = poolu(PF_IDX, q);
     const int bA = idx & 0xFF, bB = (idx >> 8) & 0xFF;
     const int pointCount = (idx >> 16) & 0xF;
@@ -990,7 +1005,7 @@ struct Sim {
   }
 
   // b2ContactSolver::SolveVelocityConstraints for one general constraint
-  __device__ __noinline__ void solveVelocityGeneral(int q) {
+  __device__ __forceinline__ void solveVelocityGeneral(int q) {
     const uint32_t idx = poolu(PF_IDX, q);
     const int bA = idx & 0xFF, bB = (idx >> 8) & 0xFF;
     const int pointCount = (idx >> 16) & 0xF;
@@ -1099,7 +1114,7 @@ struct Sim {
   }
 
   // b2ContactSolver::StoreImpulses, then re-purpose the record for the position solver
-  __device__ __noinline__ void storeGeneral(int q) {
+  __device__ __forceinline__ void storeGeneral(int q) {
     const uint32_t idx = poolu(PF_IDX, q);
     const uint32_t aux = poolu(PF_AUX, q);
     const int ci = aux & 0xFFFF;
@@ -1134,7 +1149,7 @@ struct Sim {
 
   // one general constraint of b2ContactSolver::SolvePositionConstraints / SolveTOIPositionConstraints.
   // Returns false if any point's separation is below `limit` (island not yet solved).
-  __device__ __noinline__ bool solvePositionGeneral(int q, float baumgarte, float limit, int toiA, int toiB) {
+  __device__ __forceinline__ bool solvePositionGeneral(int q, float baumgarte, float limit, int toiA, int toiB) {
     const uint32_t idx = poolu(PF_IDX, q);
     const int bA = idx & 0xFF, bB = (idx >> 8) & 0xFF;
     const int type = (idx >> 24) & 0xF;
@@ -1212,15 +1227,15 @@ struct Sim {
   }
 
   // general slot of schedule entry e (kept in the entry's otherwise unused simple record)
-  __device__ __forceinline__ int genSlot(int e) { return (int)sm[L.sRec + 8 * e]; }
+  __device__ __forceinline__ int genSlot(int e) { return (int)smp()[L.sRec + 8 * e]; }
 
   // b2World::Solve
-  __device__ void solve() {
+  __device__ __forceinline__ void solve() {
     const int nC = (int)hdr(H_NC);
     const int B = L.B;
     const int KW = L.KW;
     // ---- touching list in world-list order (descending index) and per-body masks over it
-    for (int i = g.lane; i < (B + 1) * KW; i += LPE) sm[L.sBmask + i] = 0u;
+    for (int i = g.lane; i < (B + 1) * KW; i += LPE) smp()[L.sBmask + i] = 0u;
     for (int b = g.lane; b <= B; b += LPE) {
       isl(b) = -1;
       lastLvl(b) = 0u;
@@ -1266,7 +1281,7 @@ struct Sim {
     if (g.lane == 0) {
       unsigned long long bflag = 0ull;
       int nOrd = 0, nIslands = 0, maxL = 0;
-      int32_t* stack = reinterpret_cast<int32_t*>(sm + L.sStack);
+      int32_t* stack = reinterpret_cast<int32_t*>(smp() + L.sStack);
       for (int seed = B - 1; seed >= 0; --seed) {
         if (((bflag >> seed) & 1ull) != 0ull) continue;
         if (!awake(seed)) continue;
@@ -1329,7 +1344,7 @@ struct Sim {
             hdr(H_STATUS) |= KB_STATUS_SOLVER_OVERFLOW;
             nGen = L.Gmax - 1;
           }
-          sm[L.sRec + 8 * e] = (uint32_t)nGen++;
+          smp()[L.sRec + 8 * e] = (uint32_t)nGen++;
         }
       }
       misc(0) = (uint32_t)nOrd;
@@ -1377,7 +1392,7 @@ struct Sim {
         const uint32_t item = ent(e);
         const int ci = (int)entC(e);
         if ((item & IT_GEN) != 0u) {
-          initGeneral(genSlot(e), ci, IT_BA(item), IT_BB(item), (uint32_t)ci | ((uint32_t)IT_ISL(item) << 16), false);
+          initGeneralNI(*this, genSlot(e), ci, item);
           pts += (cw(ci) & CI_PC_MASK) >> CI_PC_SHIFT;
         } else {
           initSimple(e, ci, item);
@@ -1393,7 +1408,7 @@ struct Sim {
       uint32_t item = k < nOrd ? ent(k) : IT_NONE;
       for (int r = 0; r < nRowsU; ++r) {
         if (IT_ROW(item) == r) {
-          if ((item & IT_GEN) != 0u) warmStartGeneral(genSlot(k));
+          if ((item & IT_GEN) != 0u) warmStartGeneralNI(*this, genSlot(k));
           else warmStartSimple(k, item);
           k += LPE;
           item = k < nOrd ? ent(k) : IT_NONE;
@@ -1406,7 +1421,7 @@ struct Sim {
       uint32_t item = k < nOrd ? ent(k) : IT_NONE;
       for (int r = 0; r < nRowsU; ++r) {
         if (IT_ROW(item) == r) {
-          if ((item & IT_GEN) != 0u) solveVelocityGeneral(genSlot(k));
+          if ((item & IT_GEN) != 0u) solveVelocityGeneralNI(*this, genSlot(k));
           else solveVelocitySimple(k, item);
           k += LPE;
           item = k < nOrd ? ent(k) : IT_NONE;
@@ -1415,7 +1430,7 @@ struct Sim {
       }
     }
     for (int e = g.lane; e < nOrd; e += LPE) {
-      if ((ent(e) & IT_GEN) != 0u) storeGeneral(genSlot(e));
+      if ((ent(e) & IT_GEN) != 0u) storeGeneralNI(*this, genSlot(e));
       else storeSimple(e, (int)entC(e));
     }
     // ---- integrate positions
@@ -1454,9 +1469,8 @@ struct Sim {
           if (IT_ROW(item) == r) {
             const int island = IT_ISL(item);
             if ((islflag(island) & 2u) == 0u) {
-              const bool ok = (item & IT_GEN) != 0u
-                                  ? solvePositionGeneral(genSlot(k), KB_BAUMGARTE, -3.0f * KB_LINEAR_SLOP, -1, -1)
-                                  : solvePositionSimple(k, item);
+              const bool ok = (item & IT_GEN) != 0u ? solvePositionGeneralNI(*this, genSlot(k))
+                                                    : solvePositionSimple(k, item);
               if (!ok) atomicOr(&islflag(island), 1u);
             }
             k += LPE;
@@ -1554,7 +1568,7 @@ struct Sim {
 
   // b2Body::SynchronizeFixtures + b2BroadPhase::MoveProxy for every body that was in an island
   // (toiMode: for bodies flagged in isl() by the TOI mini-island; xf1 is rebuilt from (c0, a0)).
-  __device__ void synchronizeFixtures(bool toiMode) {
+  __device__ __forceinline__ void synchronizeFixtures(bool toiMode) {
     uint32_t mlo = 0u, mhi = 0u;
     for (int p = g.lane; p < L.P; p += LPE) {
       const int b = pbody(p);
@@ -1601,7 +1615,7 @@ struct Sim {
 
   // b2BroadPhase::UpdatePairs + b2ContactManager::AddPair.  Pairs (i < j) with a moved member are
   // visited in (i, j) order == Box2D's sorted pair buffer, so creation order matches.
-  __device__ void findNewContacts() {
+  __device__ __forceinline__ void findNewContacts() {
     const uint32_t mlo = hdr(H_MOVED), mhi = hdr(H_MOVED + 1);
     g.sync();
     if ((mlo | mhi) == 0u) return;
@@ -1662,22 +1676,26 @@ struct Sim {
   }
 
   // b2World::Step(dt, velIters, posIters)
-  __device__ void worldStep() {
+  __device__ __forceinline__ void worldStep() {
     nSub += 1u;
     nCon += hdr(H_NC);
     collide();
     g.usync();
     solve();
     if (L.enableToi) {
-      solveTOI();
+      // any contact with the table at all?  (the common case is none: skip the out-of-line TOI path)
+      const int nC = (int)hdr(H_NC);
+      bool wallContact = false;
+      for (int i = g.lane; i < nC; i += LPE) wallContact |= pbody(CW_PA(cw(i))) == S;
+      if (g.any(wallContact)) nToi += solveTOINI(*this);
       g.usync();
     }
   }
 
-  __device__ void solveTOI();
+  __device__ __forceinline__ void solveTOI();   // kb_toi.cuh
 
   // ----------------------------------------------------------------------------- outputs
-  __device__ void gather(const KernelArgs& a, int env) {
+  __device__ __forceinline__ void gather(const KernelArgs& a, int env) {
     g.sync();
     const int M = L.M, N = L.N;
     bool bad = false;
@@ -1706,5 +1724,20 @@ struct Sim {
     }
   }
 };
+
+template <int LPE, bool UNI>
+__device__ __noinline__ void warmStartGeneralNI(Sim<LPE, UNI> s, int q) { s.warmStartGeneral(q); }
+template <int LPE, bool UNI>
+__device__ __noinline__ void solveVelocityGeneralNI(Sim<LPE, UNI> s, int q) { s.solveVelocityGeneral(q); }
+template <int LPE, bool UNI>
+__device__ __noinline__ bool solvePositionGeneralNI(Sim<LPE, UNI> s, int q) {
+  return s.solvePositionGeneral(q, KB_BAUMGARTE, -3.0f * KB_LINEAR_SLOP, -1, -1);
+}
+template <int LPE, bool UNI>
+__device__ __noinline__ void initGeneralNI(Sim<LPE, UNI> s, int q, int ci, uint32_t item) {
+  s.initGeneral(q, ci, IT_BA(item), IT_BB(item), (uint32_t)ci | ((uint32_t)IT_ISL(item) << 16), false);
+}
+template <int LPE, bool UNI>
+__device__ __noinline__ void storeGeneralNI(Sim<LPE, UNI> s, int q) { s.storeGeneral(q); }
 
 }  // namespace kb

@@ -429,14 +429,18 @@ __device__ __noinline__ bool time_of_impact(const ProxyConst* shapeA, SweepD swe
 
 // ------------------------------------------------------------------------ b2World::SolveTOI
 template <int LPE, bool UNI>
-__device__ __noinline__ void Sim<LPE, UNI>::solveTOI() {
+__device__ __noinline__ uint32_t solveTOINI(Sim<LPE, UNI> s) {
+  const uint32_t before = s.nToi;
+  s.solveTOI();
+  return s.nToi - before;
+}
+
+// (the caller has already established that at least one contact with the table exists)
+template <int LPE, bool UNI>
+__device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
   const int B = L.B;
   float* toi = toiCache();  // cached alpha per contact (HBM/L2; only touched when a table contact exists)
   int nC = (int)hdr(H_NC);
-  // any contact with the table at all?  (the common case is none: skip everything)
-  bool wallContact = false;
-  for (int i = g.lane; i < nC; i += LPE) wallContact |= pbody(CW_PA(cw(i))) == S;
-  if (!g.any(wallContact)) return;
 
   for (int b = g.lane; b <= B; b += LPE) reinterpret_cast<float*>(&sweep4(b))[3] = 0.0f;  // alpha0 = 0
   for (int i = g.lane; i < nC; i += LPE) {
