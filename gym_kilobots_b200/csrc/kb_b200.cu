@@ -28,14 +28,14 @@ namespace kb {
 // a real environment, so the groups of a warp can run in lock step.  Padding envs replicate the inputs of the
 // last real env and never write outputs.
 template <int LPE>
-__global__ void __launch_bounds__(KB_BLOCK) kb_step_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(KB_BLOCK, (LPE == 32 ? 8 : (LPE == 16 ? 6 : 3))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
   constexpr int EPB = KB_BLOCK / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
   const int envIn = min(env, a.numEnvs - 1);
   Sim<LPE, true> s(a.L);
   s.g.init();
-  s.sb = (uint32_t)slot * (uint32_t)a.L.smemWords;
+  s.bind(slot);
   s.blob = a.blobs + (size_t)env * a.L.blobWords;
   const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * a.L.Pp;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(KB_BLOCK) kb_reset_kernel(const __grid_constan
   const Layout& L = a.L;
   Sim<LPE, false> s(a.L);
   s.g.init();
-  s.sb = (uint32_t)slot * (uint32_t)L.smemWords;
+  s.bind(slot);
   s.blob = a.blobs + (size_t)env * L.blobWords;
   const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * L.Pp;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(KB_BLOCK) kb_reset_kernel(const __grid_constan
   s.lights = a.lights;
   s.S = L.B;
   const int lane = s.g.lane;
-  for (int i = lane; i < L.stateWords; i += LPE) s.smp()[i] = 0u;
+  for (int i = lane; i < L.stateWords; i += LPE) s.word(i) = 0u;
   for (int i = lane; i < 2 * KB_NUM_COUNTERS; i += LPE) reinterpret_cast<uint32_t*>(s.blob)[L.oCnt + i] = 0u;
   s.g.sync();
   if (lane == 0) {
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(KB_BLOCK) kb_setpose_kernel(const __grid_const
   const Layout& L = a.L;
   Sim<LPE, false> s(a.L);
   s.g.init();
-  s.sb = (uint32_t)slot * (uint32_t)L.smemWords;
+  s.bind(slot);
   s.blob = a.blobs + (size_t)env * L.blobWords;
   const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * L.Pp;

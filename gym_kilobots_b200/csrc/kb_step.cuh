@@ -86,8 +86,7 @@ template <int LPE, bool UNI>
 struct Sim {
   Group<LPE, UNI> g;
   const Layout& L;
-  uint32_t sb;                  // word offset of this env's shared-memory region in kb_smem
-  __device__ __forceinline__ uint32_t* smp() const { return kb_smem + sb; }
+  uint32_t sa;                  // shared-window byte address of this env's shared-memory region
   float* blob;                  // this env's state blob in HBM
   const ProxyConst* px;         // scene proxies
   const BodyConst* bc;          // scene bodies
@@ -99,31 +98,39 @@ struct Sim {
   __device__ __forceinline__ Sim(const Layout& l) : L(l) {
     nSub = nCon = nPts = nLvl = nPit = nToi = nTests = nIsl = 0u;
   }
+  __device__ __forceinline__ void bind(int slot) {
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(kb_smem) + (uint32_t)slot * (uint32_t)L.smemWords * 4u;
+    // opaque move: keeps the base in a register instead of re-deriving it (CTA-rank read) at every use
+    asm volatile("mov.u32 %0, %1;" : "=r"(sa) : "r"(a0));
+  }
 
-  // ---- typed views into shared memory
-  __device__ __forceinline__ float4& pos4(int b) { return reinterpret_cast<float4*>(smp() + L.oPos)[b]; }   // cx cy a sleepTime
-  __device__ __forceinline__ float4& vel4(int b) { return reinterpret_cast<float4*>(smp() + L.oVel)[b]; }   // vx vy w flags
-  __device__ __forceinline__ float4& xf4(int b) { return reinterpret_cast<float4*>(smp() + L.oXf)[b]; }     // px py qs qc
-  __device__ __forceinline__ float4& fat4(int p) { return reinterpret_cast<float4*>(smp() + L.oFat)[p]; }   // lx ly ux uy
-  __device__ __forceinline__ float4& sweep4(int b) { return reinterpret_cast<float4*>(smp() + L.sSweep)[b]; } // c0x c0y a0 alpha0
-  __device__ __forceinline__ float2& oldq(int b) { return reinterpret_cast<float2*>(smp() + L.sOldQ)[b]; }  // xf.q at step start
-  __device__ __forceinline__ float4& bc4(int b) { return reinterpret_cast<float4*>(smp() + L.sBc)[b]; }     // invMass invI lcx lcy
-  __device__ __forceinline__ float4& rec4(int i) { return reinterpret_cast<float4*>(smp() + L.sRec)[i]; }   // 2 per schedule entry
-  __device__ __forceinline__ uint32_t& cw(int i) { return smp()[L.oCw + i]; }
-  __device__ __forceinline__ uint32_t& hdr(int i) { return smp()[L.oHdr + i]; }
-  __device__ __forceinline__ int32_t& isl(int b) { return reinterpret_cast<int32_t*>(smp() + L.sIsl)[b]; }
-  __device__ __forceinline__ uint32_t& islflag(int i) { return smp()[L.sIslFlag + i]; }
-  __device__ __forceinline__ uint32_t& misc(int i) { return smp()[L.sMisc + i]; }
-  __device__ __forceinline__ uint32_t& adj(int p, int hi) { return smp()[L.sAdj + 2 * p + hi]; }
-  __device__ __forceinline__ uint32_t& bmask(int b, int w) { return smp()[L.sBmask + b * L.KW + w]; }
-  __device__ __forceinline__ uint32_t& tl(int t) { return smp()[L.sTl + t]; }
-  __device__ __forceinline__ uint32_t& ord(int p) { return smp()[L.sOrd + p]; }
-  __device__ __forceinline__ uint32_t& ent(int e) { return smp()[L.sEnt + e]; }
-  __device__ __forceinline__ uint16_t& entC(int e) { return reinterpret_cast<uint16_t*>(smp() + L.sEntC)[e]; }
-  __device__ __forceinline__ uint32_t& lvlTab(int l) { return smp()[L.sLvlTab + l]; }
-  __device__ __forceinline__ uint32_t& lastLvl(int b) { return smp()[L.sLastLvl + b]; }
-  __device__ __forceinline__ int pbody(int p) { return (int)reinterpret_cast<const uint8_t*>(smp() + L.sPb)[p]; }
-  __device__ __forceinline__ double* lightState() { return reinterpret_cast<double*>(smp() + L.oLight); }
+  // ---- typed views into shared memory (proxies standing in for references; see kb_types.cuh)
+  __device__ __forceinline__ uint32_t wa(int w) const { return sa + 4u * (uint32_t)w; }  // byte address of word w
+  __device__ __forceinline__ SU32 word(int w) const { return SU32{wa(w)}; }
+  __device__ __forceinline__ SF4 pos4(int b) const { return SF4{wa(L.oPos + 4 * b)}; }     // cx cy a sleepTime
+  __device__ __forceinline__ SF4 vel4(int b) const { return SF4{wa(L.oVel + 4 * b)}; }     // vx vy w flags
+  __device__ __forceinline__ SF4 xf4(int b) const { return SF4{wa(L.oXf + 4 * b)}; }       // px py qs qc
+  __device__ __forceinline__ SF4 fat4(int p) const { return SF4{wa(L.oFat + 4 * p)}; }     // lx ly ux uy
+  __device__ __forceinline__ SF4 sweep4(int b) const { return SF4{wa(L.sSweep + 4 * b)}; } // c0x c0y a0 alpha0
+  __device__ __forceinline__ SF2 oldq(int b) const { return SF2{wa(L.sOldQ + 2 * b)}; }    // xf.q at step start
+  __device__ __forceinline__ SF4 bc4(int b) const { return SF4{wa(L.sBc + 4 * b)}; }       // invMass invI lcx lcy
+  __device__ __forceinline__ SF4 rec4(int i) const { return SF4{wa(L.sRec + 4 * i)}; }     // 2 per schedule entry
+  __device__ __forceinline__ SU32 cw(int i) const { return SU32{wa(L.oCw + i)}; }
+  __device__ __forceinline__ SU32 hdr(int i) const { return SU32{wa(L.oHdr + i)}; }
+  __device__ __forceinline__ SI32 isl(int b) const { return SI32{wa(L.sIsl + b)}; }
+  __device__ __forceinline__ SU32 islflag(int i) const { return SU32{wa(L.sIslFlag + i)}; }
+  __device__ __forceinline__ SU32 misc(int i) const { return SU32{wa(L.sMisc + i)}; }
+  __device__ __forceinline__ SU32 adj(int p, int hi) const { return SU32{wa(L.sAdj + 2 * p + hi)}; }
+  __device__ __forceinline__ SU32 bmask(int b, int w) const { return SU32{wa(L.sBmask + b * L.KW + w)}; }
+  __device__ __forceinline__ SU32 tl(int t) const { return SU32{wa(L.sTl + t)}; }
+  __device__ __forceinline__ SU32 ord(int p) const { return SU32{wa(L.sOrd + p)}; }
+  __device__ __forceinline__ SU32 ent(int e) const { return SU32{wa(L.sEnt + e)}; }
+  __device__ __forceinline__ SU16 entC(int e) const { return SU16{wa(L.sEntC) + 2u * (uint32_t)e}; }
+  __device__ __forceinline__ SU32 lvlTab(int l) const { return SU32{wa(L.sLvlTab + l)}; }
+  __device__ __forceinline__ SU32 lastLvl(int b) const { return SU32{wa(L.sLastLvl + b)}; }
+  __device__ __forceinline__ SI32 stk(int i) const { return SI32{wa(L.sStack + i)}; }      // DFS stack / wakeAt
+  __device__ __forceinline__ int pbody(int p) const { return (int)lds_u8(wa(L.sPb) + (uint32_t)p); }
+  __device__ __forceinline__ SF64Arr lightState() const { return SF64Arr{wa(L.oLight)}; }
   // ---- HBM/L2-resident parts of the blob
   __device__ __forceinline__ double* ctrl(int k) { return reinterpret_cast<double*>(blob + L.oCtrl) + 4 * k; }
   __device__ __forceinline__ float* manifoldRec(int i) { return blob + L.oMan + MR_WORDS * i; }
@@ -140,31 +147,29 @@ struct Sim {
     t.q.c = x.w;
     return t;
   }
-  __device__ __forceinline__ bool awake(int b) { return (f2u(vel4(b).w) & BF_AWAKE) != 0u; }
+  __device__ __forceinline__ bool awake(int b) { return (f2u(vel4(b).get(3)) & BF_AWAKE) != 0u; }
   // b2Body::SetAwake(true): only acts on sleeping bodies
   __device__ __forceinline__ void wake(int b) {
     if (b == S) return;
-    uint32_t f = f2u(vel4(b).w);
+    uint32_t f = f2u(vel4(b).get(3));
     if ((f & BF_AWAKE) == 0u) {
-      reinterpret_cast<float*>(&vel4(b))[3] = u2f(f | BF_AWAKE);
-      reinterpret_cast<float*>(&pos4(b))[3] = 0.0f;
+      vel4(b).set(3, u2f(f | BF_AWAKE));
+      pos4(b).set(3, 0.0f);
     }
   }
 
   // ------------------------------------------------------------------------- state I/O
   __device__ __forceinline__ void loadState() {
     const float4* src = reinterpret_cast<const float4*>(blob);
-    float4* dst = reinterpret_cast<float4*>(smp());
     const int n4 = L.stateWords >> 2;
-    for (int i = g.lane; i < n4; i += LPE) dst[i] = src[i];
+    for (int i = g.lane; i < n4; i += LPE) sts_f4(sa + 16u * (uint32_t)i, src[i]);
     g.sync();
   }
   __device__ __forceinline__ void storeState() {
     g.sync();
     float4* dst = reinterpret_cast<float4*>(blob);
-    const float4* src = reinterpret_cast<const float4*>(smp());
     const int n4 = L.stateWords >> 2;
-    for (int i = g.lane; i < n4; i += LPE) dst[i] = src[i];
+    for (int i = g.lane; i < n4; i += LPE) dst[i] = lds_f4(sa + 16u * (uint32_t)i);
     if (g.lane == 0) {
       unsigned long long* c = reinterpret_cast<unsigned long long*>(blob + L.oCnt);
       c[KB_CNT_SUBSTEPS] += nSub;
@@ -192,15 +197,15 @@ struct Sim {
         sweep4(b) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
     }
-    for (int p = g.lane; p < L.P; p += LPE) reinterpret_cast<uint8_t*>(smp() + L.sPb)[p] = (uint8_t)__ldg(&px[p].body);
-    for (int p = g.lane; p < 2 * L.P; p += LPE) smp()[L.sAdj + p] = 0u;
+    for (int p = g.lane; p < L.P; p += LPE) sts_u8(wa(L.sPb) + (uint32_t)p, (uint32_t)__ldg(&px[p].body));
+    for (int p = g.lane; p < 2 * L.P; p += LPE) word(L.sAdj + p) = 0u;
     g.sync();
     const int nC = (int)hdr(H_NC);
     for (int i = g.lane; i < nC; i += LPE) {
       const uint32_t w = cw(i);
       const int pa = CW_PA(w), pb = CW_PB(w);
-      atomicOr(&adj(pa, pb >> 5), 1u << (pb & 31));
-      atomicOr(&adj(pb, pa >> 5), 1u << (pa & 31));
+      adj(pa, pb >> 5).atomOr(1u << (pb & 31));
+      adj(pb, pa >> 5).atomOr(1u << (pa & 31));
     }
     g.sync();
   }
@@ -212,7 +217,7 @@ struct Sim {
   }
   __device__ __forceinline__ void lightStep(const double* action) {
     if (g.lane == 0) {
-      double* ls = lightState();
+      const SF64Arr ls = lightState();
       int so = 0, ao = 0;
       for (int l = 0; l < L.numLights; ++l) {
         const LightConst& lc = lights[l];
@@ -237,14 +242,15 @@ struct Sim {
           double a1 = clipd(action[ao + 1], lc.alo[1], lc.ahi[1]);
           ls[so + 2] += a0 * dt;
           ls[so + 3] += a1 * dt;
-          double n = sqrt(ls[so + 2] * ls[so + 2] + ls[so + 3] * ls[so + 3]);
+          const double v2 = ls[so + 2], v3 = ls[so + 3];
+          double n = sqrt(v2 * v2 + v3 * v3);
           if (n > lc.maxVel) {
             double f = lc.maxVel / n;
             ls[so + 2] *= f;
             ls[so + 3] *= f;
           }
-          ls[so] += ls[so + 2] * dt;
-          ls[so + 1] += ls[so + 3] * dt;
+          ls[so] += (double)ls[so + 2] * dt;
+          ls[so + 1] += (double)ls[so + 3] * dt;
           ls[so] = clipd(ls[so], lc.blo[0], lc.bhi[0]);
           ls[so + 1] = clipd(ls[so + 1], lc.blo[1], lc.bhi[1]);
           so += 4;
@@ -263,7 +269,7 @@ struct Sim {
     g.sync();
   }
 
-  __device__ __forceinline__ void lightValueGrad(const LightConst& lc, const double* ls, double sx, double sy,
+  __device__ __forceinline__ void lightValueGrad(const LightConst& lc, const SF64Arr ls, double sx, double sy,
                                                  double* value, double* gx, double* gy) {
     if (lc.type == KB_LIGHT_LINEAR) {
       const double2 sc = kb_sincosd(ls[0]);
@@ -273,8 +279,8 @@ struct Sim {
       *gy = vy;
       return;
     }
-    double g0 = -1 * (sx - ls[0]);
-    double g1 = -1 * (sy - ls[1]);
+    double g0 = -1 * (sx - (double)ls[0]);
+    double g1 = -1 * (sy - (double)ls[1]);
     double norm = sqrt(g0 * g0 + g1 * g1);
     double v = 1.0;
     v -= norm / lc.radius;
@@ -300,13 +306,12 @@ struct Sim {
   // b2Body::SetLinearVelocity / SetAngularVelocity on a kilobot from its own lane
   __device__ __forceinline__ void setLinearVelocity(int b, V2 v) {
     if (dot(v, v) > 0.0f) wake(b);
-    float* vv = reinterpret_cast<float*>(&vel4(b));
-    vv[0] = v.x;
-    vv[1] = v.y;
+    vel4(b).set(0, v.x);
+    vel4(b).set(1, v.y);
   }
   __device__ __forceinline__ void setAngularVelocity(int b, float w) {
     if (w * w > 0.0f) wake(b);
-    reinterpret_cast<float*>(&vel4(b))[2] = w;
+    vel4(b).set(2, w);
   }
 
   __device__ __forceinline__ void setKilobotActions(const double* action) {
@@ -338,7 +343,7 @@ struct Sim {
   }
 
   __device__ __forceinline__ void senseControl() {
-    const double* ls = lightState();
+    const SF64Arr ls = lightState();
     for (int k = g.lane; k < L.N; k += LPE) {
       const int b = L.M + k;
       const int kind = __ldg(&bc[b].kind);
@@ -428,7 +433,7 @@ struct Sim {
           c[1] = c[1] < hpi ? c[1] : hpi;
         }  // fallthrough
         case KB_KILOBOT_VELOCITY: {
-          double ang = (double)pos4(b).z;
+          double ang = (double)pos4(b).get(2);
           const double2 sc = kb_sincosd(ang);
           double lx = sc.y, ly = sc.x;
           lx *= c[0] * 25.0;
@@ -518,9 +523,9 @@ struct Sim {
     bool sleepy = false;
     for (int b = g.lane; b < L.B; b += LPE) sleepy |= !awake(b);
     const bool anyAsleep = g.any(sleepy);
-    int32_t* wakeAt = reinterpret_cast<int32_t*>(smp() + L.sStack);  // reuse: per body, highest waking contact index
+    // stk(b) doubles as wakeAt[b]: per body, the highest contact index that woke it
     if (anyAsleep) {
-      for (int b = g.lane; b <= L.B; b += LPE) wakeAt[b] = awake(b) ? 0x7FFFFFFF : -1;
+      for (int b = g.lane; b <= L.B; b += LPE) stk(b) = awake(b) ? 0x7FFFFFFF : -1;
       g.sync();
     }
     bool anyDestroyed = false;
@@ -541,8 +546,8 @@ struct Sim {
             if (!anyAsleep) {
               doit = true;
             } else {
-              const bool actA = bA != S && wakeAt[bA] > i;
-              const bool actB = bB != S && wakeAt[bB] > i;
+              const bool actA = bA != S && (int32_t)stk(bA) > i;
+              const bool actB = bB != S && (int32_t)stk(bB) > i;
               doit = actA || actB;
             }
           }
@@ -555,16 +560,16 @@ struct Sim {
           if (!overlap) {
             wakeEvent = (w & CI_PC_MASK) != 0u;
             cw(i) = w | CI_DESTROY | CI_DONE;
-            atomicAnd(&adj(pa, pb >> 5), ~(1u << (pb & 31)));
-            atomicAnd(&adj(pb, pa >> 5), ~(1u << (pa & 31)));
+            adj(pa, pb >> 5).atomAnd(~(1u << (pb & 31)));
+            adj(pb, pa >> 5).atomAnd(~(1u << (pa & 31)));
             anyDestroyed = true;
           } else {
             wakeEvent = updateContact(i);
             cw(i) |= CI_DONE;
           }
           if (wakeEvent && anyAsleep) {
-            if (bA != S) atomicMax(&wakeAt[bA], i);
-            if (bB != S) atomicMax(&wakeAt[bB], i);
+            if (bA != S) stk(bA).atomMax(i);
+            if (bB != S) stk(bB).atomMax(i);
           }
         }
         progressed |= doit;
@@ -576,7 +581,7 @@ struct Sim {
     g.sync();
     if (anyAsleep) {
       for (int b = g.lane; b < L.B; b += LPE)
-        if (wakeAt[b] >= 0) wake(b);
+        if ((int32_t)stk(b) >= 0) wake(b);
       g.sync();
     }
     // clear DONE marks; stable compaction if anything was destroyed
@@ -727,13 +732,13 @@ struct Sim {
     b4.x = Bv2.x; b4.y = Bv2.y;
     vel4(bA) = a4;
     vel4(bB) = b4;
-    reinterpret_cast<float*>(&rec4(2 * e))[3] = newImpulse;
+    rec4(2 * e).set(3, newImpulse);
   }
 
   // b2ContactSolver::StoreImpulses, then re-purpose the records for the position solver
   __device__ __forceinline__ void storeSimple(int e, int ci) {
     float* rec = manifoldRec(ci);
-    rec[MR_P0N] = rec4(2 * e).w;
+    rec[MR_P0N] = rec4(2 * e).get(3);
     const float4 r0 = reinterpret_cast<const float4*>(rec)[0];
     const uint32_t tp = f2u(rec[MR_TYPE]);
     const uint32_t w = cw(ci);
@@ -964,10 +969,9 @@ struct Sim {
   }
   __device__ __forceinline__ void storeVel(int b, const VelBody& o) {
     if (b == S) return;
-    float* v = reinterpret_cast<float*>(&vel4(b));
-    v[0] = o.v.x;
-    v[1] = o.v.y;
-    v[2] = o.w;
+    vel4(b).set(0, o.v.x);
+    vel4(b).set(1, o.v.y);
+    vel4(b).set(2, o.w);
   }
 
   // b2ContactSolver::WarmStart for one general constraint
@@ -1216,18 +1220,16 @@ struct Sim {
       aB += iB * cross(rB, P);
     }
     if (bA != S) {
-      float* o = reinterpret_cast<float*>(&pos4(bA));
-      o[0] = cA.x; o[1] = cA.y; o[2] = aA;
+      pos4(bA).set(0, cA.x); pos4(bA).set(1, cA.y); pos4(bA).set(2, aA);
     }
     if (bB != S) {
-      float* o = reinterpret_cast<float*>(&pos4(bB));
-      o[0] = cB.x; o[1] = cB.y; o[2] = aB;
+      pos4(bB).set(0, cB.x); pos4(bB).set(1, cB.y); pos4(bB).set(2, aB);
     }
     return ok;
   }
 
   // general slot of schedule entry e (kept in the entry's otherwise unused simple record)
-  __device__ __forceinline__ int genSlot(int e) { return (int)smp()[L.sRec + 8 * e]; }
+  __device__ __forceinline__ int genSlot(int e) { return (int)(uint32_t)word(L.sRec + 8 * e); }
 
   // b2World::Solve
   __device__ __forceinline__ void solve() {
@@ -1235,7 +1237,7 @@ struct Sim {
     const int B = L.B;
     const int KW = L.KW;
     // ---- touching list in world-list order (descending index) and per-body masks over it
-    for (int i = g.lane; i < (B + 1) * KW; i += LPE) smp()[L.sBmask + i] = 0u;
+    for (int i = g.lane; i < (B + 1) * KW; i += LPE) word(L.sBmask + i) = 0u;
     for (int b = g.lane; b <= B; b += LPE) {
       isl(b) = -1;
       lastLvl(b) = 0u;
@@ -1265,8 +1267,8 @@ struct Sim {
       const int dst = K + __popc(m & g.lt());
       if (t && dst < L.Kmax) {
         tl(dst) = val;
-        if (bA != S) atomicOr(&bmask(bA, dst >> 5), 1u << (dst & 31));
-        if (bB != S) atomicOr(&bmask(bB, dst >> 5), 1u << (dst & 31));
+        if (bA != S) bmask(bA, dst >> 5).atomOr(1u << (dst & 31));
+        if (bB != S) bmask(bB, dst >> 5).atomOr(1u << (dst & 31));
       }
       K += __popc(m);
     }
@@ -1281,19 +1283,18 @@ struct Sim {
     if (g.lane == 0) {
       unsigned long long bflag = 0ull;
       int nOrd = 0, nIslands = 0, maxL = 0;
-      int32_t* stack = reinterpret_cast<int32_t*>(smp() + L.sStack);
       for (int seed = B - 1; seed >= 0; --seed) {
         if (((bflag >> seed) & 1ull) != 0ull) continue;
         if (!awake(seed)) continue;
         int sp = 0;
-        stack[sp++] = seed;
+        stk(sp++) = seed;
         bflag |= 1ull << seed;
         while (sp > 0) {
-          const int b = stack[--sp];
+          const int b = stk(--sp);
           isl(b) = nIslands;
           wake(b);
           for (int w = 0; w < KW; ++w) {
-            uint32_t m = bmask(b, w) & ~bmask(S, w);
+            uint32_t m = (uint32_t)bmask(b, w) & ~(uint32_t)bmask(S, w);
             if (m == 0u) continue;
             bmask(S, w) |= m;
             while (m != 0u) {
@@ -1302,7 +1303,7 @@ struct Sim {
               const uint32_t tv = tl(t);
               const int bA = (tv >> 16) & 63, bB = (tv >> 22) & 63;
               const int other = bA == b ? bB : bA;
-              const uint32_t l = max(lastLvl(bA), lastLvl(bB)) + 1u;
+              const uint32_t l = max((uint32_t)lastLvl(bA), (uint32_t)lastLvl(bB)) + 1u;
               lastLvl(bA) = l;
               lastLvl(bB) = l;
               lastLvl(S) = 0u;
@@ -1311,7 +1312,7 @@ struct Sim {
               maxL = max(maxL, (int)l);
               if (other != S && ((bflag >> other) & 1ull) == 0ull) {
                 bflag |= 1ull << other;
-                stack[sp++] = other;
+                stk(sp++) = other;
               }
             }
           }
@@ -1344,7 +1345,7 @@ struct Sim {
             hdr(H_STATUS) |= KB_STATUS_SOLVER_OVERFLOW;
             nGen = L.Gmax - 1;
           }
-          smp()[L.sRec + 8 * e] = (uint32_t)nGen++;
+          word(L.sRec + 8 * e) = (uint32_t)nGen++;
         }
       }
       misc(0) = (uint32_t)nOrd;
@@ -1471,7 +1472,7 @@ struct Sim {
             if ((islflag(island) & 2u) == 0u) {
               const bool ok = (item & IT_GEN) != 0u ? solvePositionGeneralNI(*this, genSlot(k))
                                                     : solvePositionSimple(k, item);
-              if (!ok) atomicOr(&islflag(island), 1u);
+              if (!ok) islflag(island).atomOr(1u);
             }
             k += LPE;
             item = k < nOrd ? ent(k) : IT_NONE;
@@ -1513,8 +1514,8 @@ struct Sim {
         } else {
           st = p.w + h;
         }
-        reinterpret_cast<float*>(&pos4(b))[3] = st;
-        if (!(st >= KB_TIME_TO_SLEEP)) atomicOr(&islflag(island), 4u);  // minSleepTime < timeToSleep
+        pos4(b).set(3, st);
+        if (!(st >= KB_TIME_TO_SLEEP)) islflag(island).atomOr(4u);  // minSleepTime < timeToSleep
       }
     }
     g.sync();
@@ -1525,8 +1526,8 @@ struct Sim {
         const uint32_t f = islflag(island);
         if ((f & 4u) == 0u && (f & 2u) != 0u) {
           // b2Body::SetAwake(false)
-          vel4(b) = make_float4(0.0f, 0.0f, 0.0f, u2f(f2u(vel4(b).w) & ~BF_AWAKE));
-          reinterpret_cast<float*>(&pos4(b))[3] = 0.0f;
+          vel4(b) = make_float4(0.0f, 0.0f, 0.0f, u2f(f2u(vel4(b).get(3)) & ~BF_AWAKE));
+          pos4(b).set(3, 0.0f);
         }
       }
       g.sync();
@@ -1657,8 +1658,8 @@ struct Sim {
             const int rankJ = tj == SHAPE_EDGE ? 0 : (tj == SHAPE_POLYGON ? 1 : 2);
             const int pa = rankI > rankJ ? j : i, pb = rankI > rankJ ? i : j;
             cw(dst) = (uint32_t)pa | ((uint32_t)pb << 8) | CI_ENABLED;
-            atomicOr(&adj(i, j >> 5), 1u << (j & 31));
-            atomicOr(&adj(j, i >> 5), 1u << (i & 31));
+            adj(i, j >> 5).atomOr(1u << (j & 31));
+            adj(j, i >> 5).atomOr(1u << (i & 31));
             wake(bj);
           } else {
             overflow = true;
@@ -1701,7 +1702,7 @@ struct Sim {
     bool bad = false;
     for (int b = g.lane; b < L.B; b += LPE) {
       const float4 x = xf4(b);
-      const float ang = pos4(b).z;
+      const float ang = pos4(b).get(2);
       bad |= !(isfinite(x.x) && isfinite(x.y) && isfinite(ang));
       float* o = b < M ? (a.obsObjects ? a.obsObjects + ((size_t)env * M + b) * 3 : nullptr)
                        : (a.obsKilobots ? a.obsKilobots + ((size_t)env * N + (b - M)) * 3 : nullptr);
@@ -1713,7 +1714,7 @@ struct Sim {
     }
     if (g.any(bad) && g.lane == 0) hdr(H_STATUS) |= KB_STATUS_NONFINITE;
     if (a.obsLight) {
-      const double* ls = lightState();
+      const SF64Arr ls = lightState();
       for (int i = g.lane; i < L.L; i += LPE) a.obsLight[(size_t)env * L.L + i] = ls[i];
     }
     g.sync();

@@ -442,7 +442,7 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
   float* toi = toiCache();  // cached alpha per contact (HBM/L2; only touched when a table contact exists)
   int nC = (int)hdr(H_NC);
 
-  for (int b = g.lane; b <= B; b += LPE) reinterpret_cast<float*>(&sweep4(b))[3] = 0.0f;  // alpha0 = 0
+  for (int b = g.lane; b <= B; b += LPE) sweep4(b).set(3, 0.0f);  // alpha0 = 0
   for (int i = g.lane; i < nC; i += LPE) {
     cw(i) &= ~(CI_TOI | CI_TOICOUNT_MASK);
     toi[i] = 1.0f;
@@ -451,7 +451,7 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
 
   for (int guard = 0; guard < 64 * KB_MAX_SUB_STEPS; ++guard) {
     nC = (int)hdr(H_NC);
-    const float tableAlpha0 = sweep4(S).w;
+    const float tableAlpha0 = sweep4(S).get(3);
     // ---- per-contact TOI (lane parallel).  Bodies lagging behind the table's alpha0 are
     //      advanced first (b2Sweep::Advance is idempotent for a common target).
     for (int base = 0; base < nC; base += LPE) {
@@ -552,7 +552,7 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
       Rot q = rot_set(p.z);
       V2 o = mk(p.x, p.y) - rmul(q, mk(k.z, k.w));
       xf4(bd) = make_float4(o.x, o.y, q.s, q.c);
-      reinterpret_cast<float*>(&sweep4(S))[3] = minAlpha;
+      sweep4(S).set(3, minAlpha);
       // minContact->Update()
       updateContact(minContact);
       uint32_t w = cw(minContact);
@@ -617,8 +617,7 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
       }
       {
         const float4 p = pos4(bd);
-        float* sw = reinterpret_cast<float*>(&sweep4(bd));
-        sw[0] = p.x; sw[1] = p.y; sw[2] = p.z;  // c0, a0 = corrected pose
+        sweep4(bd).set(0, p.x); sweep4(bd).set(1, p.y); sweep4(bd).set(2, p.z);  // c0, a0 = corrected pose
       }
       // velocity constraints without warm starting, at the corrected pose
       for (int k = 0; k < nIsland; ++k) initGeneral(k, (int)ord(k), S, bd, ord(k), true);
