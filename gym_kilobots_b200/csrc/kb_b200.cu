@@ -22,14 +22,15 @@
 namespace kb {
 
 // ----------------------------------------------------------------------------------- kernels
-#define KB_BLOCK 64   /* threads per block: two warps; envs per block = KB_BLOCK / LPE */
+// threads per block: two warps (one for 4-lane groups, whose 8 envs per warp already fill a block's shared memory)
+#define KB_BLOCK_OF(LPE) ((LPE) == 4 ? 32 : 64)
 
 // The batch is padded to a whole number of blocks (numEnvs <= grid * EPB): every lane of the step kernel owns
 // a real environment, so the groups of a warp can run in lock step.  Padding envs replicate the inputs of the
 // last real env and never write outputs.
 template <int LPE>
-__global__ void __launch_bounds__(KB_BLOCK, (LPE == 32 ? 8 : (LPE == 16 ? 6 : 3))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
-  constexpr int EPB = KB_BLOCK / LPE;
+__global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? 8 : (LPE == 16 ? 6 : 3))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
+  constexpr int EPB = KB_BLOCK_OF(LPE) / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
   const int envIn = min(env, a.numEnvs - 1);
@@ -59,8 +60,8 @@ __global__ void __launch_bounds__(KB_BLOCK, (LPE == 32 ? 8 : (LPE == 16 ? 6 : 3)
 }
 
 template <int LPE>
-__global__ void __launch_bounds__(KB_BLOCK) kb_reset_kernel(const __grid_constant__ KernelArgs a) {
-  constexpr int EPB = KB_BLOCK / LPE;
+__global__ void __launch_bounds__(KB_BLOCK_OF(LPE)) kb_reset_kernel(const __grid_constant__ KernelArgs a) {
+  constexpr int EPB = KB_BLOCK_OF(LPE) / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
   const int envIn = min(env, a.numEnvs - 1);
@@ -146,8 +147,8 @@ __global__ void __launch_bounds__(KB_BLOCK) kb_reset_kernel(const __grid_constan
 
 // Body.set_pose (lib/body.py:67-69) -> b2Body::SetTransform
 template <int LPE>
-__global__ void __launch_bounds__(KB_BLOCK) kb_setpose_kernel(const __grid_constant__ KernelArgs a) {
-  constexpr int EPB = KB_BLOCK / LPE;
+__global__ void __launch_bounds__(KB_BLOCK_OF(LPE)) kb_setpose_kernel(const __grid_constant__ KernelArgs a) {
+  constexpr int EPB = KB_BLOCK_OF(LPE) / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
   const int envIn = min(env, a.numEnvs - 1);
@@ -607,12 +608,16 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   L.sAdj = o; o += round4(2 * L.Pp);
   L.sPb = o; o += round4((L.Pp + 3) / 4);
   L.sBmask = o; o += round4(L.Bp * L.KW);
-  L.sTl = o; o += L.Kmax;
-  L.sOrd = o; o += L.Kmax;
   L.sEnt = o; o += L.Kmax;
   L.sEntC = o; o += round4((L.Kmax + 1) / 2);
-  L.sLvlTab = o; o += round4(L.Kmax + 2);
-  L.sRec = o; o += 8 * L.Kmax;
+  L.sGs = o; o += round4((L.Kmax + 3) / 4);
+  // the touching list, the constraint order and the level table are dead once the schedule (ent/entC) is built,
+  // which is before the first constraint record is written: they share the records' space
+  L.sRec = o;
+  L.sTl = o;
+  L.sOrd = o + L.Kmax;
+  L.sLvlTab = o + 2 * L.Kmax;
+  o += std::max(8 * L.Kmax, 2 * L.Kmax + round4(L.Kmax + 2));
   L.sMisc = o; o += 8;
   L.smemWords = round4(o);
   L.stepsPerAction = s0.steps_per_action;
@@ -647,7 +652,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     }
     L.lanesPerEnv = lpe;
   }
-  h->envsPerBlock = KB_BLOCK / L.lanesPerEnv;
+  h->envsPerBlock = KB_BLOCK_OF(L.lanesPerEnv) / L.lanesPerEnv;
   h->smemBytes = (size_t)h->envsPerBlock * L.smemWords * 4;
   if (h->smemBytes > (size_t)prop.sharedMemPerBlockOptin) {
     delete h;
@@ -754,10 +759,10 @@ int kb_get_dims(const KbHandle* hh, KbDims* d) {
 
 #define KB_LAUNCH(kernel, h, st, a)                                                               \
   switch ((h)->L.lanesPerEnv) {                                                                   \
-    case 4: kernel<4><<<launchGrid(h), KB_BLOCK, (h)->smemBytes, (st)>>>(a); break;               \
-    case 8: kernel<8><<<launchGrid(h), KB_BLOCK, (h)->smemBytes, (st)>>>(a); break;               \
-    case 16: kernel<16><<<launchGrid(h), KB_BLOCK, (h)->smemBytes, (st)>>>(a); break;             \
-    default: kernel<32><<<launchGrid(h), KB_BLOCK, (h)->smemBytes, (st)>>>(a); break;             \
+    case 4: kernel<4><<<launchGrid(h), KB_BLOCK_OF(4), (h)->smemBytes, (st)>>>(a); break;               \
+    case 8: kernel<8><<<launchGrid(h), KB_BLOCK_OF(8), (h)->smemBytes, (st)>>>(a); break;               \
+    case 16: kernel<16><<<launchGrid(h), KB_BLOCK_OF(16), (h)->smemBytes, (st)>>>(a); break;             \
+    default: kernel<32><<<launchGrid(h), KB_BLOCK_OF(32), (h)->smemBytes, (st)>>>(a); break;             \
   }
 
 int kb_reset(KbHandle* hh, const uint8_t* mask, const double* body_pose, const double* light_state,

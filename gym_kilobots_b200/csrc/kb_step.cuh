@@ -765,39 +765,51 @@ struct Sim {
     const bool trigA = bA != S && (type != MANIFOLD_CIRCLES || lp.x != 0.0f || lp.y != 0.0f || lcA.x != 0.0f ||
                                    lcA.y != 0.0f);
     const bool trigB = bB != S && (lcB.x != 0.0f || lcB.y != 0.0f);
-    Xf xfA, xfB;
-    if (trigA) xfA.q = rot_set(aA);
-    else { xfA.q.s = 0.0f; xfA.q.c = 1.0f; }
-    if (trigB) xfB.q = rot_set(aB);
-    else { xfB.q.s = 0.0f; xfB.q.c = 1.0f; }
-    xfA.p = cA - rmul(xfA.q, lcA);
-    xfB.p = cB - rmul(xfB.q, lcB);
     const V2 mpj = mk(0.0f, 0.0f);
     V2 normal, point;
     float separation;
-    if (type == MANIFOLD_CIRCLES) {
-      V2 pointA = xmul(xfA, lp);
-      V2 pointB = xmul(xfB, mpj);
-      normal = pointB - pointA;
+    if (type == MANIFOLD_CIRCLES && bA != S && !trigA && !trigB) {
+      // kilobot against kilobot: local centres and local points are all zero, so xf.p == c and
+      // b2Mul(xf, 0) == c exactly (up to the sign of a zero, which no later operation can observe).
+      // (bA == S with e_circles is a chain-vertex contact: its local point is the vertex, not zero.)
+      normal = cB - cA;
       normalize(normal);
-      point = 0.5f * (pointA + pointB);
-      separation = dot(pointB - pointA, normal) - radiusA - radiusB;
+      point = 0.5f * (cA + cB);
+      separation = dot(cB - cA, normal) - radiusA - radiusB;
     } else {
-      normal = rmul(xfA.q, ln);
-      V2 planePoint = xmul(xfA, lp);
-      V2 clipPoint = xmul(xfB, mpj);
-      separation = dot(clipPoint - planePoint, normal) - radiusA - radiusB;
-      point = clipPoint;
+      Xf xfA, xfB;
+      if (trigA) xfA.q = rot_set(aA);
+      else { xfA.q.s = 0.0f; xfA.q.c = 1.0f; }
+      if (trigB) xfB.q = rot_set(aB);
+      else { xfB.q.s = 0.0f; xfB.q.c = 1.0f; }
+      xfA.p = cA - rmul(xfA.q, lcA);
+      xfB.p = cB - rmul(xfB.q, lcB);
+      if (type == MANIFOLD_CIRCLES) {
+        V2 pointA = xmul(xfA, lp);
+        V2 pointB = xmul(xfB, mpj);
+        normal = pointB - pointA;
+        normalize(normal);
+        point = 0.5f * (pointA + pointB);
+        separation = dot(pointB - pointA, normal) - radiusA - radiusB;
+      } else {
+        normal = rmul(xfA.q, ln);
+        V2 planePoint = xmul(xfA, lp);
+        V2 clipPoint = xmul(xfB, mpj);
+        separation = dot(clipPoint - planePoint, normal) - radiusA - radiusB;
+        point = clipPoint;
+      }
     }
-    V2 rA = point - cA;
-    V2 rB = point - cB;
     const bool ok = separation >= -3.0f * KB_LINEAR_SLOP;
-    float C = b2clamp(KB_BAUMGARTE * (separation + KB_LINEAR_SLOP), -KB_MAX_LINEAR_CORRECTION, 0.0f);
-    float rnA = cross(rA, normal);
-    float rnB = cross(rB, normal);
-    float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-    float impulse = K > 0.0f ? -C / K : 0.0f;
-    V2 P = impulse * normal;
+    const float C = b2clamp(KB_BAUMGARTE * (separation + KB_LINEAR_SLOP), -KB_MAX_LINEAR_CORRECTION, 0.0f);
+    // C == 0 (not penetrating beyond the slop): the impulse is -0 / K and moves nothing
+    if (C == 0.0f) return ok;
+    const V2 rA = point - cA;
+    const V2 rB = point - cB;
+    const float rnA = cross(rA, normal);
+    const float rnB = cross(rB, normal);
+    const float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+    const float impulse = K > 0.0f ? -C / K : 0.0f;
+    const V2 P = impulse * normal;
     cA = cA - mA * P;
     aA -= iA * cross(rA, P);
     cB = cB + mB * P;
@@ -1229,7 +1241,7 @@ struct Sim {
   }
 
   // general slot of schedule entry e (kept in the entry's otherwise unused simple record)
-  __device__ __forceinline__ int genSlot(int e) { return (int)(uint32_t)word(L.sRec + 8 * e); }
+  __device__ __forceinline__ int genSlot(int e) { return (int)lds_u8(wa(L.sGs) + (uint32_t)e); }
 
   // b2World::Solve
   __device__ __forceinline__ void solve() {
@@ -1345,7 +1357,7 @@ struct Sim {
             hdr(H_STATUS) |= KB_STATUS_SOLVER_OVERFLOW;
             nGen = L.Gmax - 1;
           }
-          word(L.sRec + 8 * e) = (uint32_t)nGen++;
+          sts_u8(wa(L.sGs) + (uint32_t)e, (uint32_t)nGen++);
         }
       }
       misc(0) = (uint32_t)nOrd;

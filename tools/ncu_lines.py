@@ -42,9 +42,14 @@ def main():
             line = int(r[0])
         except ValueError:
             continue
-        inst = int(float(r[hdr["Instructions Executed"]] or 0))
-        tinst = int(float(r[hdr["Thread Instructions Executed"]] or 0))
-        smp = int(float(r[hdr["# Samples"]] or 0))
+        def num(x):
+            try:
+                return int(float(x))
+            except ValueError:
+                return 0
+        inst = num(r[hdr["Instructions Executed"]])
+        tinst = num(r[hdr["Thread Instructions Executed"]])
+        smp = num(r[hdr["# Samples"]])
         k = (cur_file, line)
         per_line[k][0] += inst
         per_line[k][1] += tinst
