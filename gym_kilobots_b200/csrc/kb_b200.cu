@@ -57,6 +57,11 @@ __global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? 8 : (LPE == 16 
   }
   if (env < a.numEnvs) s.gather(a, env);
   s.storeState();
+#ifdef KB_PROFILE
+  s.tp[12] += clock64() - s.tlast;
+  if (a.prof && s.g.lane == 0 && env < a.numEnvs)
+    for (int i = 0; i < KB_PROF_SLOTS; ++i) a.prof[(size_t)env * KB_PROF_SLOTS + i] = (unsigned long long)s.tp[i];
+#endif
 }
 
 template <int LPE>
@@ -213,6 +218,9 @@ struct Handle {
   int32_t* dStatus = nullptr;
   int envsPerBlock = 4;
   size_t smemBytes = 0;
+#ifdef KB_PROFILE
+  unsigned long long* dProf = nullptr;
+#endif
 };
 
 static int launchGrid(const Handle* h) { return (h->numEnvs + h->envsPerBlock - 1) / h->envsPerBlock; }
@@ -496,6 +504,9 @@ static void fillArgs(const Handle* h, KernelArgs* a) {
   a->scenes = h->dScenes;
   a->lights = h->dLights;
   a->numEnvs = h->numEnvs;
+#ifdef KB_PROFILE
+  a->prof = h->dProf;
+#endif
 }
 
 }  // namespace kb
@@ -553,7 +564,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   L.Cmax = round4(max_contacts > 0 ? max_contacts : std::min(P * (P - 1) / 2, 8 * B + 32));
   if (L.Cmax > 65535) L.Cmax = 65532;
   L.Kmax = round4(std::min(std::min(L.Cmax, 3 * B + 16), (int)KB_MAX_SOLVER));
-  L.KW = (L.Kmax + 31) / 32;
+  L.KW = round4((L.Kmax + 31) / 32);  // words per body mask over the touching list, padded to whole 128-bit loads
   {
     // general constraints can only arise between proxies that are not frictionless circles-with-zero-restitution
     // partners; a safe bound is every pair of object proxies plus object proxies against the table edges.  The
@@ -607,6 +618,8 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   L.sLastLvl = o; o += round4(L.Bp);
   L.sAdj = o; o += round4(2 * L.Pp);
   L.sPb = o; o += round4((L.Pp + 3) / 4);
+  L.sPt = o; o += round4((L.Pp + 3) / 4);
+  L.sPr = o; o += round4(L.Pp);
   L.sBmask = o; o += round4(L.Bp * L.KW);
   L.sEnt = o; o += L.Kmax;
   L.sEntC = o; o += round4((L.Kmax + 1) / 2);
@@ -617,7 +630,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   L.sTl = o;
   L.sOrd = o + L.Kmax;
   L.sLvlTab = o + 2 * L.Kmax;
-  o += std::max(8 * L.Kmax, 2 * L.Kmax + round4(L.Kmax + 2));
+  o += std::max(std::max(8 * L.Kmax, 2 * L.Kmax + round4(L.Kmax + 2)), 2 * L.Pp);
   L.sMisc = o; o += 8;
   L.smemWords = round4(o);
   L.stepsPerAction = s0.steps_per_action;
@@ -714,6 +727,9 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   CUDA_TRY(cudaMalloc(&h->dReward, sizeof(float) * num_envs));
   CUDA_TRY(cudaMalloc(&h->dDone, num_envs));
   CUDA_TRY(cudaMalloc(&h->dStatus, sizeof(int32_t) * num_envs));
+#ifdef KB_PROFILE
+  CUDA_TRY(cudaMalloc(&h->dProf, sizeof(unsigned long long) * KB_PROF_SLOTS * (size_t)num_envs));
+#endif
 #define KB_SET_SMEM(LPE)                                                                                            \
   case LPE:                                                                                                          \
     CUDA_TRY(cudaFuncSetAttribute(kb_step_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));   \
@@ -994,6 +1010,16 @@ int kb_set_state(KbHandle* hh, const void* in) {
   CUDA_TRY(cudaMemcpy(h->dBlobs, in, (size_t)h->numEnvs * h->L.blobWords * 4, cudaMemcpyHostToDevice));
   return KB_OK;
 }
+
+#ifdef KB_PROFILE
+// debug builds only: cycles per phase of the last kb_step, u64[E][KB_PROF_SLOTS]
+int kb_get_profile(KbHandle* hh, unsigned long long* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, h->dProf, sizeof(unsigned long long) * KB_PROF_SLOTS * (size_t)h->numEnvs, cudaMemcpyDeviceToHost));
+  return KB_OK;
+}
+#endif
 
 int kb_get_mass_data(KbHandle* hh, float* out) {
   Handle* h = reinterpret_cast<Handle*>(hh);

@@ -39,6 +39,9 @@ struct KernelArgs {
   float* reward;
   uint8_t* done;
   int32_t* status;
+#ifdef KB_PROFILE
+  unsigned long long* prof;     // [E][KB_PROF_SLOTS] cycles per phase (debug builds only)
+#endif
   // reset
   const uint8_t* mask;
   const double* pose;
@@ -72,6 +75,19 @@ struct KernelArgs {
 // addresses (a pointer kept in a struct decays to generic LD/ST).
 extern __shared__ __align__(16) uint32_t kb_smem[];
 
+// phase timers (only with -DKB_PROFILE; compiled out of the product library)
+#define KB_PROF_SLOTS 16
+#ifdef KB_PROFILE
+#define KB_T(i)                          \
+  do {                                   \
+    const long long now_ = clock64();    \
+    tp[i] += now_ - tlast;               \
+    tlast = now_;                        \
+  } while (0)
+#else
+#define KB_T(i) do { } while (0)
+#endif
+
 template <int LPE, bool UNI>
 struct Sim;
 // out-of-line (cold) paths: the Sim travels BY VALUE so that the caller's copy stays in registers
@@ -94,9 +110,16 @@ struct Sim {
   int S;                        // index of the static table in the body arrays (== L.B)
   // per-launch counter increments (lane 0's copy is flushed to the blob at the end)
   uint32_t nSub, nCon, nPts, nLvl, nPit, nToi, nTests, nIsl;
+#ifdef KB_PROFILE
+  long long tp[KB_PROF_SLOTS], tlast;
+#endif
 
   __device__ __forceinline__ Sim(const Layout& l) : L(l) {
     nSub = nCon = nPts = nLvl = nPit = nToi = nTests = nIsl = 0u;
+#ifdef KB_PROFILE
+    for (int i = 0; i < KB_PROF_SLOTS; ++i) tp[i] = 0;
+    tlast = clock64();
+#endif
   }
   __device__ __forceinline__ void bind(int slot) {
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(kb_smem) + (uint32_t)slot * (uint32_t)L.smemWords * 4u;
@@ -130,6 +153,8 @@ struct Sim {
   __device__ __forceinline__ SU32 lastLvl(int b) const { return SU32{wa(L.sLastLvl + b)}; }
   __device__ __forceinline__ SI32 stk(int i) const { return SI32{wa(L.sStack + i)}; }      // DFS stack / wakeAt
   __device__ __forceinline__ int pbody(int p) const { return (int)lds_u8(wa(L.sPb) + (uint32_t)p); }
+  __device__ __forceinline__ int ptype(int p) const { return (int)lds_u8(wa(L.sPt) + (uint32_t)p); }
+  __device__ __forceinline__ float pradius(int p) const { return lds_f32(wa(L.sPr + p)); }
   __device__ __forceinline__ SF64Arr lightState() const { return SF64Arr{wa(L.oLight)}; }
   // ---- HBM/L2-resident parts of the blob
   __device__ __forceinline__ double* ctrl(int k) { return reinterpret_cast<double*>(blob + L.oCtrl) + 4 * k; }
@@ -197,7 +222,11 @@ struct Sim {
         sweep4(b) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
     }
-    for (int p = g.lane; p < L.P; p += LPE) sts_u8(wa(L.sPb) + (uint32_t)p, (uint32_t)__ldg(&px[p].body));
+    for (int p = g.lane; p < L.P; p += LPE) {
+      sts_u8(wa(L.sPb) + (uint32_t)p, (uint32_t)__ldg(&px[p].body));
+      sts_u8(wa(L.sPt) + (uint32_t)p, (uint32_t)__ldg(&px[p].type));
+      sts_f32(wa(L.sPr + p), __ldg(&px[p].radius));
+    }
     for (int p = g.lane; p < 2 * L.P; p += LPE) word(L.sAdj + p) = 0u;
     g.sync();
     const int nC = (int)hdr(H_NC);
@@ -348,8 +377,12 @@ struct Sim {
       const int b = L.M + k;
       const int kind = __ldg(&bc[b].kind);
       const Xf xf = bodyXf(b);
+      double* c = ctrl(k);
       double value = 0.0, gx = 0.0, gy = 0.0;
-      if (L.numLights > 0) {
+      // the light is only looked at where its value can reach the controller: a PhototaxisKilobot samples
+      // on every 6th call (lib/kilobot.py:328-333), velocity / acceleration control never
+      const bool needLight = kind == KB_KILOBOT_SIMPLE_PHOTOTAXIS || (kind == KB_KILOBOT_PHOTOTAXIS && ((int)c[2] % 6) == 0);
+      if (L.numLights > 0 && needLight) {
         double sx, sy;
         if (kind == KB_KILOBOT_SIMPLE_PHOTOTAXIS) {
           sx = (double)xf.p.x / 25.0;
@@ -378,7 +411,6 @@ struct Sim {
           }
         }
       }
-      double* c = ctrl(k);
       switch (kind) {
         case KB_KILOBOT_PHOTOTAXIS: {
           // c[0] threshold, c[1] turnRight, c[2] updateCounter, c[3] noChangeCounter
@@ -451,15 +483,15 @@ struct Sim {
   __device__ __forceinline__ void evaluate(Manifold& m, int pa, int pb, int bA, int bB) {
     const ProxyConst* A = px + pa;
     const ProxyConst* Bp = px + pb;
-    const int tA = __ldg(&A->type), tB = __ldg(&Bp->type);
+    const int tA = ptype(pa), tB = ptype(pb);
     const Xf xfA = bodyXf(bA), xfB = bodyXf(bB);
     if (tA == SHAPE_CIRCLE) {
-      collide_circles(m, __ldg(&A->radius), xfA, __ldg(&Bp->radius), xfB);
+      collide_circles(m, pradius(pa), xfA, pradius(pb), xfB);
     } else if (tA == SHAPE_POLYGON) {
-      if (tB == SHAPE_CIRCLE) collide_polygon_circle(m, A, xfA, __ldg(&Bp->radius), xfB);
+      if (tB == SHAPE_CIRCLE) collide_polygon_circle(m, A, xfA, pradius(pb), xfB);
       else collide_polygons(m, A, xfA, Bp, xfB);
     } else {
-      if (tB == SHAPE_CIRCLE) collide_edge_circle(m, A, xfA, __ldg(&Bp->radius), xfB);
+      if (tB == SHAPE_CIRCLE) collide_edge_circle(m, A, xfA, pradius(pb), xfB);
       else collide_edge_polygon(m, A, xfA, Bp, xfB);
     }
   }
@@ -529,9 +561,12 @@ struct Sim {
       g.sync();
     }
     bool anyDestroyed = false;
+    // chunks from the top: a wake-up caused by a contact reaches every lower-index contact of later chunks in
+    // the same pass; another pass is only needed after a pass that woke somebody
+    const int top = ((nC - 1) / LPE) * LPE;
     for (int pass = 0;; ++pass) {
-      bool progressed = false;
-      for (int base = 0; base < nC; base += LPE) {
+      bool woke = false;
+      for (int base = top; base >= 0; base -= LPE) {
         const int i = base + g.lane;
         bool doit = false;
         int pa = 0, pb = 0, bA = S, bB = S;
@@ -559,24 +594,24 @@ struct Sim {
           bool wakeEvent;
           if (!overlap) {
             wakeEvent = (w & CI_PC_MASK) != 0u;
-            cw(i) = w | CI_DESTROY | CI_DONE;
+            cw(i) = w | CI_DESTROY | (anyAsleep ? CI_DONE : 0u);
             adj(pa, pb >> 5).atomAnd(~(1u << (pb & 31)));
             adj(pb, pa >> 5).atomAnd(~(1u << (pa & 31)));
             anyDestroyed = true;
           } else {
             wakeEvent = updateContact(i);
-            cw(i) |= CI_DONE;
+            if (anyAsleep) cw(i) |= CI_DONE;
           }
           if (wakeEvent && anyAsleep) {
             if (bA != S) stk(bA).atomMax(i);
             if (bB != S) stk(bB).atomMax(i);
+            woke = true;
           }
         }
-        progressed |= doit;
         if (anyAsleep) g.sync();
       }
       if (!anyAsleep) break;
-      if (!g.any(progressed)) break;
+      if (!g.any(woke)) break;
     }
     g.sync();
     if (anyAsleep) {
@@ -586,6 +621,7 @@ struct Sim {
     }
     // clear DONE marks; stable compaction if anything was destroyed
     const bool compact = g.any(anyDestroyed);
+    if (!compact && !anyAsleep) return;
     int out = 0;
     for (int base = 0; base < nC; base += LPE) {
       const int i = base + g.lane;
@@ -1289,42 +1325,56 @@ struct Sim {
       K = L.Kmax;
     }
     for (int l = g.lane; l <= K + 1; l += LPE) lvlTab(l) = 0u;
+    unsigned long long awakeMask = 0ull;  // awake dynamic bodies (every lane holds the whole mask)
+    for (int bb = 0; bb < B; bb += LPE) {
+      const int b = bb + g.lane;
+      awakeMask |= (unsigned long long)g.ballot(b < B && awake(b)) << bb;
+    }
     g.usync();
+    KB_T(2);
     // ---- lane 0: island DFS (b2World::Solve) in Box2D's order, dependency level of every constraint,
     //      rows, and the level-sorted schedule.  Slot S of bmask collects the contacts already in an island.
     if (g.lane == 0) {
       unsigned long long bflag = 0ull;
+      unsigned long long todo = awakeMask;  // awake dynamic bodies that are not in an island yet
       int nOrd = 0, nIslands = 0, maxL = 0;
-      for (int seed = B - 1; seed >= 0; --seed) {
-        if (((bflag >> seed) & 1ull) != 0ull) continue;
-        if (!awake(seed)) continue;
+      while (todo != 0ull) {
+        const int seed = 63 - __clzll((long long)todo);  // body list order: newest (highest index) first
+        todo &= ~(1ull << seed);
+        bflag |= 1ull << seed;
         int sp = 0;
         stk(sp++) = seed;
-        bflag |= 1ull << seed;
         while (sp > 0) {
           const int b = stk(--sp);
           isl(b) = nIslands;
-          wake(b);
-          for (int w = 0; w < KW; ++w) {
-            uint32_t m = (uint32_t)bmask(b, w) & ~(uint32_t)bmask(S, w);
-            if (m == 0u) continue;
-            bmask(S, w) |= m;
-            while (m != 0u) {
-              const int t = (w << 5) + __ffs(m) - 1;
-              m &= m - 1u;
-              const uint32_t tv = tl(t);
-              const int bA = (tv >> 16) & 63, bB = (tv >> 22) & 63;
-              const int other = bA == b ? bB : bA;
-              const uint32_t l = max((uint32_t)lastLvl(bA), (uint32_t)lastLvl(bB)) + 1u;
-              lastLvl(bA) = l;
-              lastLvl(bB) = l;
-              lastLvl(S) = 0u;
-              ord(nOrd++) = (uint32_t)t | (l << 8) | ((uint32_t)nIslands << 16);
-              lvlTab(l) += 1u;
-              maxL = max(maxL, (int)l);
-              if (other != S && ((bflag >> other) & 1ull) == 0ull) {
-                bflag |= 1ull << other;
-                stk(sp++) = other;
+          if (((awakeMask >> b) & 1ull) == 0ull) wake(b);
+          for (int w4 = 0; w4 < KW; w4 += 4) {
+            const uint4 bm = lds_u4(wa(L.sBmask + b * KW + w4));
+            const uint4 cf = lds_u4(wa(L.sBmask + S * KW + w4));
+            uint32_t mm[4] = {bm.x & ~cf.x, bm.y & ~cf.y, bm.z & ~cf.z, bm.w & ~cf.w};
+            if ((mm[0] | mm[1] | mm[2] | mm[3]) == 0u) continue;
+            sts_u4(wa(L.sBmask + S * KW + w4), make_uint4(cf.x | mm[0], cf.y | mm[1], cf.z | mm[2], cf.w | mm[3]));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t m = mm[q];
+              while (m != 0u) {
+                const int t = ((w4 + q) << 5) + __ffs(m) - 1;
+                m &= m - 1u;
+                const uint32_t tv = tl(t);
+                const int bA = (tv >> 16) & 63, bB = (tv >> 22) & 63;
+                const int other = bA == b ? bB : bA;
+                const uint32_t l = max((uint32_t)lastLvl(bA), (uint32_t)lastLvl(bB)) + 1u;
+                lastLvl(bA) = l;
+                lastLvl(bB) = l;
+                lastLvl(S) = 0u;
+                ord(nOrd++) = (uint32_t)t | (l << 8) | ((uint32_t)nIslands << 16);
+                lvlTab(l) += 1u;
+                maxL = max(maxL, (int)l);
+                if (other != S && ((bflag >> other) & 1ull) == 0ull) {
+                  bflag |= 1ull << other;
+                  todo &= ~(1ull << other);
+                  stk(sp++) = other;
+                }
               }
             }
           }
@@ -1368,6 +1418,7 @@ struct Sim {
     g.usync();
     const int nOrd = (int)misc(0), nRows = (int)misc(1), nIslands = (int)misc(2);
     const int nRowsU = g.umax(nRows);  // warp-uniform row count: the groups of a warp sweep their rows in lock step
+    KB_T(3);
     nIsl += (uint32_t)nIslands;
     nLvl += misc(3);
     // ---- b2Island::Solve: integrate velocities (damping), remember the sweep start
@@ -1415,6 +1466,7 @@ struct Sim {
       nPts += g.red_add(pts);
     }
     g.usync();
+    KB_T(4);
     // warm start, then velocity iterations: a lane walks its entries in row order
     {
       int k = g.lane;
@@ -1442,6 +1494,7 @@ struct Sim {
         g.usync();
       }
     }
+    KB_T(5);
     for (int e = g.lane; e < nOrd; e += LPE) {
       if ((ent(e) & IT_GEN) != 0u) storeGeneralNI(*this, genSlot(e));
       else storeSimple(e, (int)entC(e));
@@ -1470,6 +1523,7 @@ struct Sim {
     }
     for (int i = g.lane; i < nIslands; i += LPE) islflag(i) = 0u;  // bit0: unsolved this iteration, bit1: solved
     g.usync();
+    KB_T(6);
     // ---- position iterations with per-island early exit
     {
       int remaining = nIslands;
@@ -1507,6 +1561,7 @@ struct Sim {
         g.usync();
       }
     }
+    KB_T(7);
     // ---- copy back: SynchronizeTransform; sleep bookkeeping
     for (int b = g.lane; b < B; b += LPE) {
       const int island = isl(b);
@@ -1545,9 +1600,12 @@ struct Sim {
       g.sync();
     }
     g.usync();
+    KB_T(8);
     synchronizeFixtures(false);
+    KB_T(9);
     findNewContacts();
     g.usync();
+    KB_T(10);
   }
 
   // shape AABB of proxy p under transform xf (b2Shape::ComputeAABB)
@@ -1627,7 +1685,11 @@ struct Sim {
   }
 
   // b2BroadPhase::UpdatePairs + b2ContactManager::AddPair.  Pairs (i < j) with a moved member are
-  // visited in (i, j) order == Box2D's sorted pair buffer, so creation order matches.
+  // created in (i, j) order == Box2D's sorted pair buffer, so creation order matches.  A lane owns a
+  // row i: it tests the columns j > i that need testing (row or column moved, no contact yet) and
+  // collects the new pairs in a 64-bit mask; an exclusive scan over the rows of a chunk gives every
+  // row its place in the contact list.  Rows are independent: a new pair (i, j) never changes what a
+  // later row has to test.
   __device__ __forceinline__ void findNewContacts() {
     const uint32_t mlo = hdr(H_MOVED), mhi = hdr(H_MOVED + 1);
     g.sync();
@@ -1636,51 +1698,65 @@ struct Sim {
       hdr(H_MOVED) = 0u;
       hdr(H_MOVED + 1) = 0u;
     }
-    const unsigned long long moved = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
+    const int P = L.P;
+    const unsigned long long valid = P >= 64 ? ~0ull : ((1ull << P) - 1ull);
+    const unsigned long long moved = ((unsigned long long)mlo | ((unsigned long long)mhi << 32)) & valid;
     int nC = (int)hdr(H_NC);
     bool overflow = false;
     uint32_t tests = 0u;
-    const int P = L.P;
-    for (int i = 0; i < P - 1; ++i) {
-      const bool movedI = ((moved >> i) & 1ull) != 0ull;
-      if (!movedI && (moved >> (i + 1)) == 0ull) break;
-      const float4 fi = fat4(i);
-      const int bi = pbody(i);
-      const int ti = __ldg(&px[i].type);
-      const unsigned long long adjI = (unsigned long long)adj(i, 0) | ((unsigned long long)adj(i, 1) << 32);
-      for (int jb = i + 1; jb < P; jb += LPE) {
-        const int j = jb + g.lane;
-        bool create = false;
-        int bj = S, tj = 0;
-        if (j < P && (movedI || ((moved >> j) & 1ull) != 0ull)) {
-          ++tests;
-          const float4 fj = fat4(j);
-          const bool overlap = !(fj.x - fi.z > 0.0f || fj.y - fi.w > 0.0f || fi.x - fj.z > 0.0f || fi.y - fj.w > 0.0f);
-          bj = pbody(j);
-          create = overlap && bi != bj && ((adjI >> j) & 1ull) == 0ull;
+    for (int ib = 0; ib < P - 1; ib += LPE) {
+      if ((moved >> ib) == 0ull) break;  // neither a row from here on nor any of their columns moved
+      const int i = ib + g.lane;
+      unsigned long long cand = 0ull;
+      int bi = S;
+      if (i < P - 1) {
+        const bool movedI = ((moved >> i) & 1ull) != 0ull;
+        unsigned long long cols = (movedI ? valid : moved) & (~0ull << (i + 1));
+        if (cols != 0ull) {
+          tests += (uint32_t)__popcll(cols);
+          cols &= ~((unsigned long long)(uint32_t)adj(i, 0) | ((unsigned long long)(uint32_t)adj(i, 1) << 32));
+          if (cols != 0ull) {
+            const float4 fi = fat4(i);
+            bi = pbody(i);
+            while (cols != 0ull) {
+              const int j = __ffsll((long long)cols) - 1;
+              cols &= cols - 1ull;
+              const float4 fj = fat4(j);
+              // b2TestOverlap
+              const bool overlap = !(fj.x - fi.z > 0.0f || fj.y - fi.w > 0.0f || fi.x - fj.z > 0.0f || fi.y - fj.w > 0.0f);
+              if (overlap && pbody(j) != bi) cand |= 1ull << j;
+            }
+          }
         }
-        const uint32_t m = g.ballot(create);
-        if (m == 0u) continue;
-        const int dst = nC + __popc(m & g.lt());
-        if (create) {
+      }
+      const int cnt = __popcll(cand);
+      if (!g.any(cnt != 0)) continue;
+      const int off = g.exscan(cnt);
+      const int total = g.bcast(off + cnt, LPE - 1);
+      if (cnt != 0) {
+        int dst = nC + off;
+        const int ti = ptype(i);
+        const int rankI = ti == SHAPE_EDGE ? 0 : (ti == SHAPE_POLYGON ? 1 : 2);
+        wake(bi);
+        while (cand != 0ull) {
+          const int j = __ffsll((long long)cand) - 1;
+          cand &= cand - 1ull;
           if (dst < L.Cmax) {
             // type register: chain edge < polygon < circle takes the A slot (b2Contact::Create)
-            tj = __ldg(&px[j].type);
-            const int rankI = ti == SHAPE_EDGE ? 0 : (ti == SHAPE_POLYGON ? 1 : 2);
+            const int tj = ptype(j);
             const int rankJ = tj == SHAPE_EDGE ? 0 : (tj == SHAPE_POLYGON ? 1 : 2);
             const int pa = rankI > rankJ ? j : i, pb = rankI > rankJ ? i : j;
             cw(dst) = (uint32_t)pa | ((uint32_t)pb << 8) | CI_ENABLED;
             adj(i, j >> 5).atomOr(1u << (j & 31));
             adj(j, i >> 5).atomOr(1u << (i & 31));
-            wake(bj);
+            wake(pbody(j));
           } else {
             overflow = true;
           }
+          ++dst;
         }
-        if (g.lane == 0 && bi != S) wake(bi);
-        nC = min(nC + __popc(m), L.Cmax);
-        g.sync();
       }
+      nC = min(nC + total, L.Cmax);
     }
     nTests += g.red_add(tests);
     if (g.lane == 0) hdr(H_NC) = (uint32_t)nC;
@@ -1692,8 +1768,10 @@ struct Sim {
   __device__ __forceinline__ void worldStep() {
     nSub += 1u;
     nCon += hdr(H_NC);
+    KB_T(0);
     collide();
     g.usync();
+    KB_T(1);
     solve();
     if (L.enableToi) {
       // any contact with the table at all?  (the common case is none: skip the out-of-line TOI path)
@@ -1702,6 +1780,7 @@ struct Sim {
       for (int i = g.lane; i < nC; i += LPE) wallContact |= pbody(CW_PA(cw(i))) == S;
       if (g.any(wallContact)) nToi += solveTOINI(*this);
       g.usync();
+      KB_T(11);
     }
   }
 
