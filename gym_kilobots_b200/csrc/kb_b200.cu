@@ -43,6 +43,10 @@ __global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? 8 : (LPE == 16 
   s.bc = a.bodies + (size_t)scene * a.L.Bp;
   s.lights = a.lights;
   s.S = a.L.B;
+#ifdef KB_PROFILE
+  s.profOut = a.prof ? a.prof + (size_t)envIn * KB_PROF_SLOTS : nullptr;
+  if (s.profOut && s.g.lane == 0) s.profOut[13] = s.profOut[14] = s.profOut[15] = 0ull;
+#endif
   s.loadState();
   s.initScratch();
   const int A = a.actionMode == KB_ACTION_KILOBOTS ? 2 * a.L.N : a.L.A;
@@ -60,7 +64,7 @@ __global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? 8 : (LPE == 16 
 #ifdef KB_PROFILE
   s.tp[12] += clock64() - s.tlast;
   if (a.prof && s.g.lane == 0 && env < a.numEnvs)
-    for (int i = 0; i < KB_PROF_SLOTS; ++i) a.prof[(size_t)env * KB_PROF_SLOTS + i] = (unsigned long long)s.tp[i];
+    for (int i = 0; i < 13; ++i) a.prof[(size_t)env * KB_PROF_SLOTS + i] = (unsigned long long)s.tp[i];
 #endif
 }
 

@@ -40,7 +40,7 @@ __device__ __forceinline__ void collide_circles(Manifold& m, float rA, Xf xfA, f
   m.id[0] = 0u;
 }
 
-__device__ __noinline__ void collide_polygon_circle(Manifold& m, const ProxyConst* __restrict__ polyA, Xf xfA,
+__device__ __forceinline__ void collide_polygon_circle(Manifold& m, const ProxyConst* __restrict__ polyA, Xf xfA,
                                                     float circleRadius, Xf xfB) {
   m.pointCount = 0;
   V2 c = xmul(xfB, mk(0.0f, 0.0f));
@@ -231,7 +231,7 @@ __device__ __noinline__ void collide_polygons(Manifold& m, const ProxyConst* __r
 }
 
 // edge vertices of a chain child: vx/vy[0..3] = v0, v1, v2, v3
-__device__ __noinline__ void collide_edge_circle(Manifold& m, const ProxyConst* __restrict__ edgeA, Xf xfA,
+__device__ __forceinline__ void collide_edge_circle(Manifold& m, const ProxyConst* __restrict__ edgeA, Xf xfA,
                                                  float circleRadius, Xf xfB) {
   m.pointCount = 0;
   V2 Q = xmulT(xfA, xmul(xfB, mk(0.0f, 0.0f)));

@@ -112,6 +112,7 @@ struct Sim {
   uint32_t nSub, nCon, nPts, nLvl, nPit, nToi, nTests, nIsl;
 #ifdef KB_PROFILE
   long long tp[KB_PROF_SLOTS], tlast;
+  unsigned long long* profOut;   // this env's row of the profile buffer (TOI internals add to slots 13..15 directly)
 #endif
 
   __device__ __forceinline__ Sim(const Layout& l) : L(l) {
@@ -485,14 +486,27 @@ struct Sim {
     const ProxyConst* Bp = px + pb;
     const int tA = ptype(pa), tB = ptype(pb);
     const Xf xfA = bodyXf(bA), xfB = bodyXf(bB);
-    if (tA == SHAPE_CIRCLE) {
-      collide_circles(m, pradius(pa), xfA, pradius(pb), xfB);
-    } else if (tA == SHAPE_POLYGON) {
-      if (tB == SHAPE_CIRCLE) collide_polygon_circle(m, A, xfA, pradius(pb), xfB);
-      else collide_polygons(m, A, xfA, Bp, xfB);
+    // every contact of a kilobot is one of the three inlined cases: their manifold stays in registers.  The
+    // polygon cases (object against object / table) run out of line on a temporary, the only manifold whose
+    // address is ever taken (local memory costs an L2 round trip here: shared memory takes most of the L1).
+    if (tB == SHAPE_CIRCLE) {
+      if (tA == SHAPE_CIRCLE) collide_circles(m, pradius(pa), xfA, pradius(pb), xfB);
+      else if (tA == SHAPE_POLYGON) collide_polygon_circle(m, A, xfA, pradius(pb), xfB);
+      else collide_edge_circle(m, A, xfA, pradius(pb), xfB);
     } else {
-      if (tB == SHAPE_CIRCLE) collide_edge_circle(m, A, xfA, pradius(pb), xfB);
-      else collide_edge_polygon(m, A, xfA, Bp, xfB);
+      Manifold t;
+      t.pointCount = 0;
+      t.type = 0;
+      t.lnx = t.lny = t.lpx = t.lpy = 0.0f;
+      t.px[0] = t.py[0] = t.px[1] = t.py[1] = 0.0f;
+      t.id[0] = t.id[1] = 0u;
+      if (tA == SHAPE_POLYGON) collide_polygons(t, A, xfA, Bp, xfB);
+      else collide_edge_polygon(t, A, xfA, Bp, xfB);
+      m.pointCount = t.pointCount;
+      m.type = t.type;
+      m.lnx = t.lnx; m.lny = t.lny; m.lpx = t.lpx; m.lpy = t.lpy;
+      m.px[0] = t.px[0]; m.py[0] = t.py[0]; m.px[1] = t.px[1]; m.py[1] = t.py[1];
+      m.id[0] = t.id[0]; m.id[1] = t.id[1];
     }
   }
 

@@ -12,12 +12,22 @@ namespace kb {
 struct SweepD {
   V2 lc, c0, c;
   float a0, a, alpha0;
+  // the rotation of this sweep cannot influence the result, so b2Rot::Set (double-precision sin/cos here)
+  // is skipped and q = (0, 1) is used: either a0 == a == 0, where (0, 1) IS the exact rotation (the table),
+  // or the shape is a circle centred on a body whose local centre is zero (a kilobot), where q only ever
+  // multiplies exact zeros and picks the support vertex of a one-vertex proxy
+  int fixedRot;
 };
 __device__ __forceinline__ Xf sweep_xf(const SweepD& s, float beta) {
   Xf xf;
   xf.p = (1.0f - beta) * s.c0 + beta * s.c;
   float angle = (1.0f - beta) * s.a0 + beta * s.a;
-  xf.q = rot_set(angle);
+  if (s.fixedRot) {
+    xf.q.s = 0.0f;
+    xf.q.c = 1.0f;
+  } else {
+    xf.q = rot_set(angle);
+  }
   xf.p = xf.p - rmul(xf.q, s.lc);
   return xf;
 }
@@ -58,10 +68,13 @@ struct DProxy {
   }
 };
 
+// Everything below is written without arrays, references into callers' frames or pointers to locals: the
+// simplex, its cache and the separation function live in registers.  (Local memory is an L2 round trip in this
+// kernel -- shared memory takes most of the L1 -- and b2Distance is a chain of dependent accesses.)
 struct SimplexCache {
   float metric;
   int count;
-  int indexA[3], indexB[3];
+  int iA0, iA1, iA2, iB0, iB1, iB2;
 };
 struct SimplexVertex {
   V2 wA, wB, w;
@@ -69,291 +82,283 @@ struct SimplexVertex {
   int indexA, indexB;
 };
 
-struct Simplex {
-  SimplexVertex v[3];
-  int count;
-
-  __device__ float metric() const {
-    if (count == 2) return length(v[0].w - v[1].w);
-    if (count == 3) return cross(v[1].w - v[0].w, v[2].w - v[0].w);
-    return 0.0f;
+__device__ __forceinline__ float simplex_metric(int count, const SimplexVertex& v0, const SimplexVertex& v1,
+                                                const SimplexVertex& v2) {
+  if (count == 2) return length(v0.w - v1.w);
+  if (count == 3) return cross(v1.w - v0.w, v2.w - v0.w);
+  return 0.0f;
+}
+__device__ __forceinline__ void simplex_solve2(int& count, SimplexVertex& v0, SimplexVertex& v1) {
+  V2 w1 = v0.w, w2 = v1.w;
+  V2 e12 = w2 - w1;
+  float d12_2 = -dot(w1, e12);
+  if (d12_2 <= 0.0f) {
+    v0.a = 1.0f;
+    count = 1;
+    return;
   }
-  __device__ void solve2() {
-    V2 w1 = v[0].w, w2 = v[1].w;
-    V2 e12 = w2 - w1;
-    float d12_2 = -dot(w1, e12);
-    if (d12_2 <= 0.0f) {
-      v[0].a = 1.0f;
-      count = 1;
-      return;
-    }
-    float d12_1 = dot(w2, e12);
-    if (d12_1 <= 0.0f) {
-      v[1].a = 1.0f;
-      count = 1;
-      v[0] = v[1];
-      return;
-    }
+  float d12_1 = dot(w2, e12);
+  if (d12_1 <= 0.0f) {
+    v1.a = 1.0f;
+    count = 1;
+    v0 = v1;
+    return;
+  }
+  float inv_d12 = 1.0f / (d12_1 + d12_2);
+  v0.a = d12_1 * inv_d12;
+  v1.a = d12_2 * inv_d12;
+  count = 2;
+}
+__device__ __forceinline__ void simplex_solve3(int& count, SimplexVertex& v0, SimplexVertex& v1, SimplexVertex& v2) {
+  V2 w1 = v0.w, w2 = v1.w, w3 = v2.w;
+  V2 e12 = w2 - w1;
+  float w1e12 = dot(w1, e12);
+  float w2e12 = dot(w2, e12);
+  float d12_1 = w2e12;
+  float d12_2 = -w1e12;
+  V2 e13 = w3 - w1;
+  float w1e13 = dot(w1, e13);
+  float w3e13 = dot(w3, e13);
+  float d13_1 = w3e13;
+  float d13_2 = -w1e13;
+  V2 e23 = w3 - w2;
+  float w2e23 = dot(w2, e23);
+  float w3e23 = dot(w3, e23);
+  float d23_1 = w3e23;
+  float d23_2 = -w2e23;
+  float n123 = cross(e12, e13);
+  float d123_1 = n123 * cross(w2, w3);
+  float d123_2 = n123 * cross(w3, w1);
+  float d123_3 = n123 * cross(w1, w2);
+  if (d12_2 <= 0.0f && d13_2 <= 0.0f) {
+    v0.a = 1.0f;
+    count = 1;
+    return;
+  }
+  if (d12_1 > 0.0f && d12_2 > 0.0f && d123_3 <= 0.0f) {
     float inv_d12 = 1.0f / (d12_1 + d12_2);
-    v[0].a = d12_1 * inv_d12;
-    v[1].a = d12_2 * inv_d12;
+    v0.a = d12_1 * inv_d12;
+    v1.a = d12_2 * inv_d12;
     count = 2;
+    return;
   }
-  __device__ void solve3() {
-    V2 w1 = v[0].w, w2 = v[1].w, w3 = v[2].w;
-    V2 e12 = w2 - w1;
-    float w1e12 = dot(w1, e12);
-    float w2e12 = dot(w2, e12);
-    float d12_1 = w2e12;
-    float d12_2 = -w1e12;
-    V2 e13 = w3 - w1;
-    float w1e13 = dot(w1, e13);
-    float w3e13 = dot(w3, e13);
-    float d13_1 = w3e13;
-    float d13_2 = -w1e13;
-    V2 e23 = w3 - w2;
-    float w2e23 = dot(w2, e23);
-    float w3e23 = dot(w3, e23);
-    float d23_1 = w3e23;
-    float d23_2 = -w2e23;
-    float n123 = cross(e12, e13);
-    float d123_1 = n123 * cross(w2, w3);
-    float d123_2 = n123 * cross(w3, w1);
-    float d123_3 = n123 * cross(w1, w2);
-    if (d12_2 <= 0.0f && d13_2 <= 0.0f) {
-      v[0].a = 1.0f;
-      count = 1;
-      return;
-    }
-    if (d12_1 > 0.0f && d12_2 > 0.0f && d123_3 <= 0.0f) {
-      float inv_d12 = 1.0f / (d12_1 + d12_2);
-      v[0].a = d12_1 * inv_d12;
-      v[1].a = d12_2 * inv_d12;
-      count = 2;
-      return;
-    }
-    if (d13_1 > 0.0f && d13_2 > 0.0f && d123_2 <= 0.0f) {
-      float inv_d13 = 1.0f / (d13_1 + d13_2);
-      v[0].a = d13_1 * inv_d13;
-      v[2].a = d13_2 * inv_d13;
-      count = 2;
-      v[1] = v[2];
-      return;
-    }
-    if (d12_1 <= 0.0f && d23_2 <= 0.0f) {
-      v[1].a = 1.0f;
-      count = 1;
-      v[0] = v[1];
-      return;
-    }
-    if (d13_1 <= 0.0f && d23_1 <= 0.0f) {
-      v[2].a = 1.0f;
-      count = 1;
-      v[0] = v[2];
-      return;
-    }
-    if (d23_1 > 0.0f && d23_2 > 0.0f && d123_1 <= 0.0f) {
-      float inv_d23 = 1.0f / (d23_1 + d23_2);
-      v[1].a = d23_1 * inv_d23;
-      v[2].a = d23_2 * inv_d23;
-      count = 2;
-      v[0] = v[2];
-      return;
-    }
-    float inv_d123 = 1.0f / (d123_1 + d123_2 + d123_3);
-    v[0].a = d123_1 * inv_d123;
-    v[1].a = d123_2 * inv_d123;
-    v[2].a = d123_3 * inv_d123;
-    count = 3;
+  if (d13_1 > 0.0f && d13_2 > 0.0f && d123_2 <= 0.0f) {
+    float inv_d13 = 1.0f / (d13_1 + d13_2);
+    v0.a = d13_1 * inv_d13;
+    v2.a = d13_2 * inv_d13;
+    count = 2;
+    v1 = v2;
+    return;
   }
-};
+  if (d12_1 <= 0.0f && d23_2 <= 0.0f) {
+    v1.a = 1.0f;
+    count = 1;
+    v0 = v1;
+    return;
+  }
+  if (d13_1 <= 0.0f && d23_1 <= 0.0f) {
+    v2.a = 1.0f;
+    count = 1;
+    v0 = v2;
+    return;
+  }
+  if (d23_1 > 0.0f && d23_2 > 0.0f && d123_1 <= 0.0f) {
+    float inv_d23 = 1.0f / (d23_1 + d23_2);
+    v1.a = d23_1 * inv_d23;
+    v2.a = d23_2 * inv_d23;
+    count = 2;
+    v0 = v2;
+    return;
+  }
+  float inv_d123 = 1.0f / (d123_1 + d123_2 + d123_3);
+  v0.a = d123_1 * inv_d123;
+  v1.a = d123_2 * inv_d123;
+  v2.a = d123_3 * inv_d123;
+  count = 3;
+}
+
+__device__ __forceinline__ SimplexVertex simplex_vertex(const DProxy& pA, Xf tA, const DProxy& pB, Xf tB, int ia, int ib) {
+  SimplexVertex sv;
+  sv.indexA = ia;
+  sv.indexB = ib;
+  sv.wA = xmul(tA, pA.vertex(ia));
+  sv.wB = xmul(tB, pB.vertex(ib));
+  sv.w = sv.wB - sv.wA;
+  sv.a = 0.0f;
+  return sv;
+}
 
 // b2Distance(useRadii = false): distance between the core shapes; updates the cache.
-__device__ __noinline__ float gjk_distance(SimplexCache& cache, const DProxy& pA, Xf tA, const DProxy& pB, Xf tB) {
-  Simplex s;
-  s.count = cache.count;
-  for (int i = 0; i < s.count; ++i) {
-    SimplexVertex& sv = s.v[i];
-    sv.indexA = cache.indexA[i];
-    sv.indexB = cache.indexB[i];
-    sv.wA = xmul(tA, pA.vertex(sv.indexA));
-    sv.wB = xmul(tB, pB.vertex(sv.indexB));
-    sv.w = sv.wB - sv.wA;
-    sv.a = 0.0f;
-  }
-  if (s.count > 1) {
+__device__ __forceinline__ float gjk_distance(SimplexCache& cache, const DProxy& pA, Xf tA, const DProxy& pB, Xf tB) {
+  SimplexVertex v0, v1, v2;
+  int count = cache.count;
+  v0 = simplex_vertex(pA, tA, pB, tB, count > 0 ? cache.iA0 : 0, count > 0 ? cache.iB0 : 0);
+  v1 = v0;
+  v2 = v0;
+  if (count > 1) v1 = simplex_vertex(pA, tA, pB, tB, cache.iA1, cache.iB1);
+  if (count > 2) v2 = simplex_vertex(pA, tA, pB, tB, cache.iA2, cache.iB2);
+  if (count > 1) {
     float metric1 = cache.metric;
-    float metric2 = s.metric();
-    if (metric2 < 0.5f * metric1 || 2.0f * metric1 < metric2 || metric2 < KB_EPS) s.count = 0;
+    float metric2 = simplex_metric(count, v0, v1, v2);
+    if (metric2 < 0.5f * metric1 || 2.0f * metric1 < metric2 || metric2 < KB_EPS) count = 0;
   }
-  if (s.count == 0) {
-    SimplexVertex& sv = s.v[0];
-    sv.indexA = 0;
-    sv.indexB = 0;
-    sv.wA = xmul(tA, pA.vertex(0));
-    sv.wB = xmul(tB, pB.vertex(0));
-    sv.w = sv.wB - sv.wA;
-    sv.a = 1.0f;
-    s.count = 1;
+  if (count == 0) {
+    v0 = simplex_vertex(pA, tA, pB, tB, 0, 0);
+    v0.a = 1.0f;
+    count = 1;
   }
   const int k_maxIters = 20;
-  int saveA[3], saveB[3];
   int iter = 0;
   while (iter < k_maxIters) {
-    int saveCount = s.count;
-    for (int i = 0; i < saveCount; ++i) {
-      saveA[i] = s.v[i].indexA;
-      saveB[i] = s.v[i].indexB;
-    }
-    if (s.count == 2) s.solve2();
-    else if (s.count == 3) s.solve3();
-    if (s.count == 3) break;
+    const int saveCount = count;
+    const int sA0 = v0.indexA, sB0 = v0.indexB, sA1 = v1.indexA, sB1 = v1.indexB, sA2 = v2.indexA, sB2 = v2.indexB;
+    if (count == 2) simplex_solve2(count, v0, v1);
+    else if (count == 3) simplex_solve3(count, v0, v1, v2);
+    if (count == 3) break;
     // search direction
     V2 d;
-    if (s.count == 1) {
-      d = -s.v[0].w;
+    if (count == 1) {
+      d = -v0.w;
     } else {
-      V2 e12 = s.v[1].w - s.v[0].w;
-      float sgn = cross(e12, -s.v[0].w);
+      V2 e12 = v1.w - v0.w;
+      float sgn = cross(e12, -v0.w);
       d = sgn > 0.0f ? cross(1.0f, e12) : cross(e12, 1.0f);
     }
     if (dot(d, d) < KB_EPS * KB_EPS) break;
-    SimplexVertex& nv = s.v[s.count];
+    SimplexVertex nv;
     nv.indexA = pA.support(rmulT(tA.q, -d));
     nv.wA = xmul(tA, pA.vertex(nv.indexA));
     nv.indexB = pB.support(rmulT(tB.q, d));
     nv.wB = xmul(tB, pB.vertex(nv.indexB));
     nv.w = nv.wB - nv.wA;
+    nv.a = 0.0f;
     ++iter;
-    bool duplicate = false;
-    for (int i = 0; i < saveCount; ++i) {
-      if (nv.indexA == saveA[i] && nv.indexB == saveB[i]) {
-        duplicate = true;
-        break;
-      }
-    }
+    const bool duplicate = (saveCount > 0 && nv.indexA == sA0 && nv.indexB == sB0) ||
+                           (saveCount > 1 && nv.indexA == sA1 && nv.indexB == sB1) ||
+                           (saveCount > 2 && nv.indexA == sA2 && nv.indexB == sB2);
     if (duplicate) break;
-    ++s.count;
+    if (count == 1) v1 = nv;
+    else v2 = nv;
+    ++count;
   }
   V2 pointA, pointB;
-  if (s.count == 1) {
-    pointA = s.v[0].wA;
-    pointB = s.v[0].wB;
-  } else if (s.count == 2) {
-    pointA = s.v[0].a * s.v[0].wA + s.v[1].a * s.v[1].wA;
-    pointB = s.v[0].a * s.v[0].wB + s.v[1].a * s.v[1].wB;
+  if (count == 1) {
+    pointA = v0.wA;
+    pointB = v0.wB;
+  } else if (count == 2) {
+    pointA = v0.a * v0.wA + v1.a * v1.wA;
+    pointB = v0.a * v0.wB + v1.a * v1.wB;
   } else {
-    pointA = s.v[0].a * s.v[0].wA + s.v[1].a * s.v[1].wA + s.v[2].a * s.v[2].wA;
+    pointA = v0.a * v0.wA + v1.a * v1.wA + v2.a * v2.wA;
     pointB = pointA;
   }
   float distance = length(pointA - pointB);
-  cache.metric = s.metric();
-  cache.count = s.count;
-  for (int i = 0; i < s.count; ++i) {
-    cache.indexA[i] = s.v[i].indexA;
-    cache.indexB[i] = s.v[i].indexB;
-  }
+  cache.metric = simplex_metric(count, v0, v1, v2);
+  cache.count = count;
+  cache.iA0 = v0.indexA; cache.iB0 = v0.indexB;
+  cache.iA1 = v1.indexA; cache.iB1 = v1.indexB;
+  cache.iA2 = v2.indexA; cache.iB2 = v2.indexB;
   return distance;
 }
 
 // b2SeparationFunction
 struct SepFn {
-  const DProxy* pA;
-  const DProxy* pB;
+  DProxy pA, pB;
   SweepD sA, sB;
   int type;  // 0 points, 1 faceA, 2 faceB
   V2 localPoint, axis;
 
-  __device__ void initialize(const SimplexCache& cache, const DProxy* a, const SweepD& sa, const DProxy* b,
-                             const SweepD& sb, float t1) {
+  __device__ __forceinline__ void initialize(const SimplexCache& cache, const DProxy& a, const SweepD& sa,
+                                             const DProxy& b, const SweepD& sb, float t1) {
     pA = a;
     pB = b;
     sA = sa;
     sB = sb;
+    localPoint = mk(0.0f, 0.0f);
     Xf xfA = sweep_xf(sA, t1), xfB = sweep_xf(sB, t1);
     if (cache.count == 1) {
       type = 0;
-      V2 pointA = xmul(xfA, pA->vertex(cache.indexA[0]));
-      V2 pointB = xmul(xfB, pB->vertex(cache.indexB[0]));
+      V2 pointA = xmul(xfA, pA.vertex(cache.iA0));
+      V2 pointB = xmul(xfB, pB.vertex(cache.iB0));
       axis = pointB - pointA;
       normalize(axis);
-    } else if (cache.indexA[0] == cache.indexA[1]) {
+    } else if (cache.iA0 == cache.iA1) {
       type = 2;
-      V2 localPointB1 = pB->vertex(cache.indexB[0]);
-      V2 localPointB2 = pB->vertex(cache.indexB[1]);
+      V2 localPointB1 = pB.vertex(cache.iB0);
+      V2 localPointB2 = pB.vertex(cache.iB1);
       axis = cross(localPointB2 - localPointB1, 1.0f);
       normalize(axis);
       V2 normal = rmul(xfB.q, axis);
       localPoint = 0.5f * (localPointB1 + localPointB2);
       V2 pointB = xmul(xfB, localPoint);
-      V2 pointA = xmul(xfA, pA->vertex(cache.indexA[0]));
+      V2 pointA = xmul(xfA, pA.vertex(cache.iA0));
       float s = dot(pointA - pointB, normal);
       if (s < 0.0f) axis = -axis;
     } else {
       type = 1;
-      V2 localPointA1 = pA->vertex(cache.indexA[0]);
-      V2 localPointA2 = pA->vertex(cache.indexA[1]);
+      V2 localPointA1 = pA.vertex(cache.iA0);
+      V2 localPointA2 = pA.vertex(cache.iA1);
       axis = cross(localPointA2 - localPointA1, 1.0f);
       normalize(axis);
       V2 normal = rmul(xfA.q, axis);
       localPoint = 0.5f * (localPointA1 + localPointA2);
       V2 pointA = xmul(xfA, localPoint);
-      V2 pointB = xmul(xfB, pB->vertex(cache.indexB[0]));
+      V2 pointB = xmul(xfB, pB.vertex(cache.iB0));
       float s = dot(pointB - pointA, normal);
       if (s < 0.0f) axis = -axis;
     }
   }
-  __device__ float findMinSeparation(int* indexA, int* indexB, float t) const {
+  __device__ __forceinline__ float findMinSeparation(int& indexA, int& indexB, float t) const {
     Xf xfA = sweep_xf(sA, t), xfB = sweep_xf(sB, t);
     if (type == 0) {
       V2 axisA = rmulT(xfA.q, axis);
       V2 axisB = rmulT(xfB.q, -axis);
-      *indexA = pA->support(axisA);
-      *indexB = pB->support(axisB);
-      V2 pointA = xmul(xfA, pA->vertex(*indexA));
-      V2 pointB = xmul(xfB, pB->vertex(*indexB));
+      indexA = pA.support(axisA);
+      indexB = pB.support(axisB);
+      V2 pointA = xmul(xfA, pA.vertex(indexA));
+      V2 pointB = xmul(xfB, pB.vertex(indexB));
       return dot(pointB - pointA, axis);
     } else if (type == 1) {
       V2 normal = rmul(xfA.q, axis);
       V2 pointA = xmul(xfA, localPoint);
       V2 axisB = rmulT(xfB.q, -normal);
-      *indexA = -1;
-      *indexB = pB->support(axisB);
-      V2 pointB = xmul(xfB, pB->vertex(*indexB));
+      indexA = -1;
+      indexB = pB.support(axisB);
+      V2 pointB = xmul(xfB, pB.vertex(indexB));
       return dot(pointB - pointA, normal);
     } else {
       V2 normal = rmul(xfB.q, axis);
       V2 pointB = xmul(xfB, localPoint);
       V2 axisA = rmulT(xfA.q, -normal);
-      *indexB = -1;
-      *indexA = pA->support(axisA);
-      V2 pointA = xmul(xfA, pA->vertex(*indexA));
+      indexB = -1;
+      indexA = pA.support(axisA);
+      V2 pointA = xmul(xfA, pA.vertex(indexA));
       return dot(pointA - pointB, normal);
     }
   }
-  __device__ float evaluate(int indexA, int indexB, float t) const {
+  __device__ __forceinline__ float evaluate(int indexA, int indexB, float t) const {
     Xf xfA = sweep_xf(sA, t), xfB = sweep_xf(sB, t);
     if (type == 0) {
-      V2 pointA = xmul(xfA, pA->vertex(indexA));
-      V2 pointB = xmul(xfB, pB->vertex(indexB));
+      V2 pointA = xmul(xfA, pA.vertex(indexA));
+      V2 pointB = xmul(xfB, pB.vertex(indexB));
       return dot(pointB - pointA, axis);
     } else if (type == 1) {
       V2 normal = rmul(xfA.q, axis);
       V2 pointA = xmul(xfA, localPoint);
-      V2 pointB = xmul(xfB, pB->vertex(indexB));
+      V2 pointB = xmul(xfB, pB.vertex(indexB));
       return dot(pointB - pointA, normal);
     } else {
       V2 normal = rmul(xfB.q, axis);
       V2 pointB = xmul(xfB, localPoint);
-      V2 pointA = xmul(xfA, pA->vertex(indexA));
+      V2 pointA = xmul(xfA, pA.vertex(indexA));
       return dot(pointA - pointB, normal);
     }
   }
 };
 
-// b2TimeOfImpact with tMax = 1.  Returns true and *t if the state is e_touching.
-__device__ __noinline__ bool time_of_impact(const ProxyConst* shapeA, SweepD sweepA, const ProxyConst* shapeB,
-                                            SweepD sweepB, float* tOut) {
+// b2TimeOfImpact with tMax = 1.  Returns t >= 0 if the state is e_touching, a negative value otherwise.
+__device__ __noinline__ float time_of_impact(const ProxyConst* shapeA, SweepD sweepA, const ProxyConst* shapeB,
+                                             SweepD sweepB) {
   DProxy proxyA, proxyB;
   proxyA.set(shapeA);
   proxyB.set(shapeB);
@@ -369,33 +374,28 @@ __device__ __noinline__ bool time_of_impact(const ProxyConst* shapeA, SweepD swe
   SimplexCache cache;
   cache.metric = 0.0f;
   cache.count = 0;
+  cache.iA0 = cache.iA1 = cache.iA2 = cache.iB0 = cache.iB1 = cache.iB2 = 0;
   for (;;) {
     Xf xfA = sweep_xf(sweepA, t1), xfB = sweep_xf(sweepB, t1);
     float distance = gjk_distance(cache, proxyA, xfA, proxyB, xfB);
-    if (distance <= 0.0f) return false;  // e_overlapped
-    if (distance < target + tolerance) {
-      *tOut = t1;
-      return true;  // e_touching
-    }
+    if (distance <= 0.0f) return -1.0f;  // e_overlapped
+    if (distance < target + tolerance) return t1;  // e_touching
     SepFn fcn;
-    fcn.initialize(cache, &proxyA, sweepA, &proxyB, sweepB, t1);
+    fcn.initialize(cache, proxyA, sweepA, proxyB, sweepB, t1);
     bool done = false;
     float t2 = tMax;
     int pushBackIter = 0;
     for (;;) {
       int indexA, indexB;
-      float s2 = fcn.findMinSeparation(&indexA, &indexB, t2);
-      if (s2 > target + tolerance) return false;  // e_separated
+      float s2 = fcn.findMinSeparation(indexA, indexB, t2);
+      if (s2 > target + tolerance) return -1.0f;  // e_separated
       if (s2 > target - tolerance) {
         t1 = t2;
         break;
       }
       float s1 = fcn.evaluate(indexA, indexB, t1);
-      if (s1 < target - tolerance) return false;  // e_failed
-      if (s1 <= target + tolerance) {
-        *tOut = t1;
-        return true;  // e_touching
-      }
+      if (s1 < target - tolerance) return -1.0f;  // e_failed
+      if (s1 <= target + tolerance) return t1;  // e_touching
       int rootIterCount = 0;
       float a1 = t1, a2 = t2;
       for (;;) {
@@ -422,9 +422,9 @@ __device__ __noinline__ bool time_of_impact(const ProxyConst* shapeA, SweepD swe
     }
     ++iter;
     if (done) break;
-    if (iter == k_maxIterations) return false;  // e_failed
+    if (iter == k_maxIterations) return -1.0f;  // e_failed
   }
-  return false;
+  return -1.0f;
 }
 
 // ------------------------------------------------------------------------ b2World::SolveTOI
@@ -450,6 +450,10 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
   g.sync();
 
   for (int guard = 0; guard < 64 * KB_MAX_SUB_STEPS; ++guard) {
+#ifdef KB_PROFILE
+    long long tq0 = clock64();
+    if (profOut && g.lane == 0) profOut[15] += 1ull;   // rounds
+#endif
     nC = (int)hdr(H_NC);
     const float tableAlpha0 = sweep4(S).get(3);
     // ---- per-contact TOI (lane parallel).  Bodies lagging behind the table's alpha0 are
@@ -494,17 +498,25 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
         SweepD sA, sB;
         sA.lc = mk(0.0f, 0.0f); sA.c0 = mk(0.0f, 0.0f); sA.c = mk(0.0f, 0.0f);
         sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = tableAlpha0;
+        sA.fixedRot = 1;
         sB.lc = mk(k.z, k.w); sB.c0 = mk(sw.x, sw.y); sB.c = mk(p.x, p.y);
         sB.a0 = sw.z; sB.a = p.z; sB.alpha0 = sw.w;
+        sB.fixedRot = (ptype(pb) == SHAPE_CIRCLE && k.z == 0.0f && k.w == 0.0f) ? 1 : 0;
         const float alpha0 = tableAlpha0;
-        float beta = 1.0f;
         float alpha = 1.0f;
-        if (time_of_impact(px + pa, sA, px + pb, sB, &beta)) alpha = b2min(alpha0 + (1.0f - alpha0) * beta, 1.0f);
+        {
+          const float t = time_of_impact(px + pa, sA, px + pb, sB);
+          if (t >= 0.0f) alpha = b2min(alpha0 + (1.0f - alpha0) * t, 1.0f);
+        }
         toi[i] = alpha;
         cw(i) |= CI_TOI;
       }
       g.sync();
     }
+#ifdef KB_PROFILE
+    if (profOut && g.lane == 0) profOut[13] += (unsigned long long)(clock64() - tq0);   // TOI computations
+    tq0 = clock64();
+#endif
     // ---- minimum alpha, first in world-list order (highest index) on ties
     uint32_t bestBits = f2u(1.0f);
     int bestIdx = -1;
@@ -664,6 +676,9 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
     const int after = (int)hdr(H_NC);
     for (int i = before + g.lane; i < after; i += LPE) toi[i] = 1.0f;
     g.sync();
+#ifdef KB_PROFILE
+    if (profOut && g.lane == 0) profOut[14] += (unsigned long long)(clock64() - tq0);   // event handling
+#endif
   }
 }
 
