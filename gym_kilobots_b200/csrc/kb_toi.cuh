@@ -38,7 +38,10 @@ __device__ __forceinline__ void sweep_normalize(SweepD& s) {
   s.a -= d;
 }
 
-// b2DistanceProxy over a scene proxy
+// b2DistanceProxy over a scene proxy.  Three flavours with one interface: the generic one reads the template
+// at run time; the edge and circle ones fix vertex count and vertex access at compile time, so that the by far
+// most common continuous-collision pair (table edge against a kilobot) compiles to short straight-line code
+// with its two edge vertices in registers -- same arithmetic, a fraction of the instructions and branches.
 struct DProxy {
   const ProxyConst* pc;
   int type, count;
@@ -65,6 +68,30 @@ struct DProxy {
       }
     }
     return bestIndex;
+  }
+};
+struct DProxyEdge {
+  V2 e1, e2;
+  float radius;
+  __device__ __forceinline__ void set(const ProxyConst* p) {
+    e1 = pvert(p, 1);
+    e2 = pvert(p, 2);
+    radius = __ldg(&p->radius);
+  }
+  __device__ __forceinline__ V2 vertex(int i) const { return i == 0 ? e1 : e2; }
+  __device__ __forceinline__ int support(V2 d) const {
+    const float bestValue = dot(e1, d);
+    const float value = dot(e2, d);
+    return value > bestValue ? 1 : 0;
+  }
+};
+struct DProxyCircle {
+  float radius;
+  __device__ __forceinline__ void set(const ProxyConst* p) { radius = __ldg(&p->radius); }
+  __device__ __forceinline__ V2 vertex(int) const { return mk(0.0f, 0.0f); }
+  __device__ __forceinline__ int support(V2 d) const {
+    (void)dot(mk(0.0f, 0.0f), d);
+    return 0;
   }
 };
 
@@ -177,7 +204,8 @@ __device__ __forceinline__ void simplex_solve3(int& count, SimplexVertex& v0, Si
   count = 3;
 }
 
-__device__ __forceinline__ SimplexVertex simplex_vertex(const DProxy& pA, Xf tA, const DProxy& pB, Xf tB, int ia, int ib) {
+template <class PA, class PB>
+__device__ __forceinline__ SimplexVertex simplex_vertex(const PA& pA, Xf tA, const PB& pB, Xf tB, int ia, int ib) {
   SimplexVertex sv;
   sv.indexA = ia;
   sv.indexB = ib;
@@ -189,7 +217,8 @@ __device__ __forceinline__ SimplexVertex simplex_vertex(const DProxy& pA, Xf tA,
 }
 
 // b2Distance(useRadii = false): distance between the core shapes; updates the cache.
-__device__ __forceinline__ float gjk_distance(SimplexCache& cache, const DProxy& pA, Xf tA, const DProxy& pB, Xf tB) {
+template <class PA, class PB>
+__device__ __forceinline__ float gjk_distance(SimplexCache& cache, const PA& pA, Xf tA, const PB& pB, Xf tB) {
   SimplexVertex v0, v1, v2;
   int count = cache.count;
   v0 = simplex_vertex(pA, tA, pB, tB, count > 0 ? cache.iA0 : 0, count > 0 ? cache.iB0 : 0);
@@ -262,14 +291,16 @@ __device__ __forceinline__ float gjk_distance(SimplexCache& cache, const DProxy&
 }
 
 // b2SeparationFunction
+template <class PA, class PB>
 struct SepFn {
-  DProxy pA, pB;
+  PA pA;
+  PB pB;
   SweepD sA, sB;
   int type;  // 0 points, 1 faceA, 2 faceB
   V2 localPoint, axis;
 
-  __device__ __forceinline__ void initialize(const SimplexCache& cache, const DProxy& a, const SweepD& sa,
-                                             const DProxy& b, const SweepD& sb, float t1) {
+  __device__ __forceinline__ void initialize(const SimplexCache& cache, const PA& a, const SweepD& sa, const PB& b,
+                                             const SweepD& sb, float t1) {
     pA = a;
     pB = b;
     sA = sa;
@@ -357,9 +388,11 @@ struct SepFn {
 };
 
 // b2TimeOfImpact with tMax = 1.  Returns t >= 0 if the state is e_touching, a negative value otherwise.
-__device__ __noinline__ float time_of_impact(const ProxyConst* shapeA, SweepD sweepA, const ProxyConst* shapeB,
-                                             SweepD sweepB) {
-  DProxy proxyA, proxyB;
+template <class PA, class PB>
+__device__ __forceinline__ float time_of_impact_t(const ProxyConst* shapeA, SweepD sweepA, const ProxyConst* shapeB,
+                                                  SweepD sweepB) {
+  PA proxyA;
+  PB proxyB;
   proxyA.set(shapeA);
   proxyB.set(shapeB);
   sweep_normalize(sweepA);
@@ -380,7 +413,7 @@ __device__ __noinline__ float time_of_impact(const ProxyConst* shapeA, SweepD sw
     float distance = gjk_distance(cache, proxyA, xfA, proxyB, xfB);
     if (distance <= 0.0f) return -1.0f;  // e_overlapped
     if (distance < target + tolerance) return t1;  // e_touching
-    SepFn fcn;
+    SepFn<PA, PB> fcn;
     fcn.initialize(cache, proxyA, sweepA, proxyB, sweepB, t1);
     bool done = false;
     float t2 = tMax;
@@ -425,6 +458,16 @@ __device__ __noinline__ float time_of_impact(const ProxyConst* shapeA, SweepD sw
     if (iter == k_maxIterations) return -1.0f;  // e_failed
   }
   return -1.0f;
+}
+
+__device__ __noinline__ float time_of_impact(const ProxyConst* shapeA, SweepD sweepA, const ProxyConst* shapeB,
+                                             SweepD sweepB) {
+  return time_of_impact_t<DProxy, DProxy>(shapeA, sweepA, shapeB, sweepB);
+}
+// table edge against a circle (a kilobot or a Circle object)
+__device__ __noinline__ float time_of_impact_edge_circle(const ProxyConst* shapeA, SweepD sweepA, const ProxyConst* shapeB,
+                                                         SweepD sweepB) {
+  return time_of_impact_t<DProxyEdge, DProxyCircle>(shapeA, sweepA, shapeB, sweepB);
 }
 
 // ------------------------------------------------------------------------ b2World::SolveTOI
@@ -505,7 +548,9 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
         const float alpha0 = tableAlpha0;
         float alpha = 1.0f;
         {
-          const float t = time_of_impact(px + pa, sA, px + pb, sB);
+          const float t = (ptype(pa) == SHAPE_EDGE && ptype(pb) == SHAPE_CIRCLE)
+                              ? time_of_impact_edge_circle(px + pa, sA, px + pb, sB)
+                              : time_of_impact(px + pa, sA, px + pb, sB);
           if (t >= 0.0f) alpha = b2min(alpha0 + (1.0f - alpha0) * t, 1.0f);
         }
         toi[i] = alpha;
