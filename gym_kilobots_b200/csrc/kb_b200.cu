@@ -628,6 +628,9 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   L.sPb = o; o += round4((L.Pp + 3) / 4);
   L.sPt = o; o += round4((L.Pp + 3) / 4);
   L.sPr = o; o += round4(L.Pp);
+  L.sBk = o; o += round4((L.Bp + 3) / 4);
+  L.sDamp = o; o += round4(2 * L.Bp);
+  L.sLc = o; o += round4(LC_WORDS * std::max((int)s0.num_lights, 1));
   L.sBmask = o; o += round4(L.Bp * L.KW);
   L.sEnt = o; o += L.Kmax;
   L.sEntC = o; o += round4((L.Kmax + 1) / 2);

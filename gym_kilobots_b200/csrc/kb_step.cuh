@@ -80,6 +80,7 @@ extern __shared__ __align__(16) uint32_t kb_smem[];
 #ifdef KB_PROFILE
 #define KB_T(i)                          \
   do {                                   \
+    if (UNI) __syncthreads();            \
     const long long now_ = clock64();    \
     tp[i] += now_ - tlast;               \
     tlast = now_;                        \
@@ -158,7 +159,12 @@ struct Sim {
   __device__ __forceinline__ SU32 lastLvl(int b) const { return SU32{wa(L.sLastLvl + b)}; }
   __device__ __forceinline__ SI32 stk(int i) const { return SI32{wa(L.sStack + i)}; }      // DFS stack / wakeAt
   __device__ __forceinline__ int pbody(int p) const { return (int)lds_u8(wa(L.sPb) + (uint32_t)p); }
-  __device__ __forceinline__ int ptype(int p) const { return (int)lds_u8(wa(L.sPt) + (uint32_t)p); }
+  // proxy flags: bits 0-1 shape type, bit 2 friction == 0, bit 3 restitution == 0
+  __device__ __forceinline__ int pflags(int p) const { return (int)lds_u8(wa(L.sPt) + (uint32_t)p); }
+  __device__ __forceinline__ int ptype(int p) const { return pflags(p) & 3; }
+  __device__ __forceinline__ int bkind(int b) const { return (int)lds_u8(wa(L.sBk) + (uint32_t)b); }
+  __device__ __forceinline__ SF2 damp(int b) const { return SF2{wa(L.sDamp + 2 * b)}; }  // velocity damping factors
+  __device__ __forceinline__ LCs lightConst(int l) const { return LCs{wa(L.sLc + LC_WORDS * l)}; }
   __device__ __forceinline__ float pradius(int p) const { return lds_f32(wa(L.sPr + p)); }
   __device__ __forceinline__ SF64Arr lightState() const { return SF64Arr{wa(L.oLight)}; }
   // ---- HBM/L2-resident parts of the blob
@@ -219,6 +225,12 @@ struct Sim {
       if (b < L.B) {
         const BodyConst* c = bc + b;
         bc4(b) = make_float4(__ldg(&c->invMass), __ldg(&c->invI), __ldg(&c->lcx), __ldg(&c->lcy));
+        sts_u8(wa(L.sBk) + (uint32_t)b, (uint32_t)__ldg(&c->kind));
+        // b2Island::Solve damping factors (SimplePhototaxisKilobot's linearDamping = 0, lib/kilobot.py:203, is
+        // folded into the template)
+        const float h = L.dt, ld = __ldg(&c->linearDamping), ad = __ldg(&c->angularDamping);
+        damp(b) = L.dampingMode == 0 ? make_float2(1.0f / (1.0f + h * ld), 1.0f / (1.0f + h * ad))
+                                     : make_float2(b2clamp(1.0f - h * ld, 0.0f, 1.0f), b2clamp(1.0f - h * ad, 0.0f, 1.0f));
       } else {
         bc4(b) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         pos4(b) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -229,10 +241,13 @@ struct Sim {
     }
     for (int p = g.lane; p < L.P; p += LPE) {
       sts_u8(wa(L.sPb) + (uint32_t)p, (uint32_t)__ldg(&px[p].body));
-      sts_u8(wa(L.sPt) + (uint32_t)p, (uint32_t)__ldg(&px[p].type));
+      sts_u8(wa(L.sPt) + (uint32_t)p, (uint32_t)__ldg(&px[p].type) | (__ldg(&px[p].friction) == 0.0f ? 4u : 0u) |
+                                          (__ldg(&px[p].restitution) == 0.0f ? 8u : 0u));
       sts_f32(wa(L.sPr + p), __ldg(&px[p].radius));
     }
     for (int p = g.lane; p < 2 * L.P; p += LPE) word(L.sAdj + p) = 0u;
+    for (int w = g.lane; w < LC_WORDS * L.numLights; w += LPE)
+      word(L.sLc + w) = __ldg(reinterpret_cast<const uint32_t*>(lights) + w);
     g.sync();
     const int nC = (int)hdr(H_NC);
     for (int i = g.lane; i < nC; i += LPE) {
@@ -254,43 +269,45 @@ struct Sim {
       const SF64Arr ls = lightState();
       int so = 0, ao = 0;
       for (int l = 0; l < L.numLights; ++l) {
-        const LightConst& lc = lights[l];
-        if (lc.type == KB_LIGHT_CIRCULAR) {
-          double a0 = clipd(action[ao], lc.alo[0], lc.ahi[0]);
-          double a1 = clipd(action[ao + 1], lc.alo[1], lc.ahi[1]);
+        const LCs lc = lightConst(l);
+        const int lt = lc.type();
+        if (lt == KB_LIGHT_CIRCULAR) {
+          double a0 = clipd(action[ao], lc.alo(0), lc.ahi(0));
+          double a1 = clipd(action[ao + 1], lc.alo(1), lc.ahi(1));
           const double dt = 1. / 10;
-          if (lc.relative) {
+          if (lc.relative()) {
             ls[so] += a0 * dt;
             ls[so + 1] += a1 * dt;
           } else {
             ls[so] = a0;
             ls[so + 1] = a1;
           }
-          ls[so] = clipd(ls[so], lc.blo[0], lc.bhi[0]);
-          ls[so + 1] = clipd(ls[so + 1], lc.blo[1], lc.bhi[1]);
+          ls[so] = clipd(ls[so], lc.blo(0), lc.bhi(0));
+          ls[so + 1] = clipd(ls[so + 1], lc.blo(1), lc.bhi(1));
           so += 2;
           ao += 2;
-        } else if (lc.type == KB_LIGHT_MOMENTUM) {
+        } else if (lt == KB_LIGHT_MOMENTUM) {
           const double dt = 1. / 10;
-          double a0 = clipd(action[ao], lc.alo[0], lc.ahi[0]);
-          double a1 = clipd(action[ao + 1], lc.alo[1], lc.ahi[1]);
+          double a0 = clipd(action[ao], lc.alo(0), lc.ahi(0));
+          double a1 = clipd(action[ao + 1], lc.alo(1), lc.ahi(1));
           ls[so + 2] += a0 * dt;
           ls[so + 3] += a1 * dt;
           const double v2 = ls[so + 2], v3 = ls[so + 3];
           double n = sqrt(v2 * v2 + v3 * v3);
-          if (n > lc.maxVel) {
-            double f = lc.maxVel / n;
+          const double mv = lc.maxVel();
+          if (n > mv) {
+            double f = mv / n;
             ls[so + 2] *= f;
             ls[so + 3] *= f;
           }
           ls[so] += (double)ls[so + 2] * dt;
           ls[so + 1] += (double)ls[so + 3] * dt;
-          ls[so] = clipd(ls[so], lc.blo[0], lc.bhi[0]);
-          ls[so + 1] = clipd(ls[so + 1], lc.blo[1], lc.bhi[1]);
+          ls[so] = clipd(ls[so], lc.blo(0), lc.bhi(0));
+          ls[so + 1] = clipd(ls[so + 1], lc.blo(1), lc.bhi(1));
           so += 4;
           ao += 2;
         } else {
-          double a = clipd(action[ao], lc.alo[0], lc.ahi[0]);
+          double a = clipd(action[ao], lc.alo(0), lc.ahi(0));
           const double pi = 3.141592653589793;
           if (a < -pi) a += 2 * pi;
           if (a > pi) a -= 2 * pi;
@@ -303,9 +320,9 @@ struct Sim {
     g.sync();
   }
 
-  __device__ __forceinline__ void lightValueGrad(const LightConst& lc, const SF64Arr ls, double sx, double sy,
+  __device__ __forceinline__ void lightValueGrad(const LCs lc, const SF64Arr ls, double sx, double sy,
                                                  double* value, double* gx, double* gy) {
-    if (lc.type == KB_LIGHT_LINEAR) {
+    if (lc.type() == KB_LIGHT_LINEAR) {
       const double2 sc = kb_sincosd(ls[0]);
       const double vx = sc.y, vy = sc.x;
       *value = vx * sx + vy * sy;
@@ -317,7 +334,8 @@ struct Sim {
     double g1 = -1 * (sy - (double)ls[1]);
     double norm = sqrt(g0 * g0 + g1 * g1);
     double v = 1.0;
-    v -= norm / lc.radius;
+    const double radius = lc.radius();
+    v -= norm / radius;
     v = v < 1. ? v : 1.;
     v = v > .0 ? v : .0;
     v *= 255;
@@ -328,7 +346,7 @@ struct Sim {
       g0 /= norm;
       g1 /= norm;
     }
-    if (norm > lc.radius) {
+    if (norm > radius) {
       g0 *= .0;
       g1 *= .0;
     }
@@ -352,7 +370,7 @@ struct Sim {
     const double hpi = 0.5 * 3.141592653589793;
     const double pi = 3.141592653589793;
     for (int k = g.lane; k < L.N; k += LPE) {
-      const int kind = __ldg(&bc[L.M + k].kind);
+      const int kind = bkind(L.M + k);
       double* c = ctrl(k);
       const double* a = action ? action + 2 * k : nullptr;
       if (kind == KB_KILOBOT_VELOCITY) {
@@ -380,7 +398,7 @@ struct Sim {
     const SF64Arr ls = lightState();
     for (int k = g.lane; k < L.N; k += LPE) {
       const int b = L.M + k;
-      const int kind = __ldg(&bc[b].kind);
+      const int kind = bkind(b);
       const Xf xf = bodyXf(b);
       double* c = ctrl(k);
       double value = 0.0, gx = 0.0, gy = 0.0;
@@ -399,20 +417,21 @@ struct Sim {
           sy = (double)wp.y / 25.0;
         }
         if (L.numLights == 1) {
-          lightValueGrad(lights[0], ls, sx, sy, &value, &gx, &gy);
+          lightValueGrad(lightConst(0), ls, sx, sy, &value, &gx, &gy);
         } else {
           double best = 0.0;
           int so = 0;
           for (int l = 0; l < L.numLights; ++l) {
             double v, g0, g1;
-            lightValueGrad(lights[l], ls + so, sx, sy, &v, &g0, &g1);
+            lightValueGrad(lightConst(l), ls + so, sx, sy, &v, &g0, &g1);
             value += v;
             if (l == 0 || v > best) {
               best = v;
               gx = g0;
               gy = g1;
             }
-            so += lights[l].type == KB_LIGHT_MOMENTUM ? 4 : (lights[l].type == KB_LIGHT_LINEAR ? 1 : 2);
+            const int lt = lightConst(l).type();
+            so += lt == KB_LIGHT_MOMENTUM ? 4 : (lt == KB_LIGHT_LINEAR ? 1 : 2);
           }
         }
       }
@@ -697,7 +716,7 @@ struct Sim {
     const float4* rec = reinterpret_cast<const float4*>(manifoldRec(ci));
     const float4 r0 = rec[0], r1 = rec[1];
     const int type = (int)(f2u(manifoldRec(ci)[MR_TYPE]) & 0xFFu);
-    const float radiusA = __ldg(&px[pa].radius), radiusB = __ldg(&px[pb].radius);
+    const float radiusA = pradius(pa), radiusB = pradius(pb);
     const float4 cA4 = pos4(bA), cB4 = pos4(bB);
     const float4 kA = bc4(bA), kB = bc4(bB);
     const float mA = kA.x, iA = kA.y, mB = kB.x, iB = kB.y;
@@ -797,7 +816,7 @@ struct Sim {
     const uint32_t tp = f2u(rec[MR_TYPE]);
     const uint32_t w = cw(ci);
     rec4(2 * e) = r0;
-    rec4(2 * e + 1) = make_float4(__ldg(&px[CW_PA(w)].radius), __ldg(&px[CW_PB(w)].radius), u2f(tp & 0xFFu), 0.0f);
+    rec4(2 * e + 1) = make_float4(pradius(CW_PA(w)), pradius(CW_PB(w)), u2f(tp & 0xFFu), 0.0f);
   }
 
   // one constraint of b2ContactSolver::SolvePositionConstraints.  Returns false if the separation is
@@ -891,7 +910,7 @@ struct Sim {
     const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
     const uint32_t tp = f2u(r3.z);
     const int type = tp & 0xFF, pointCount = (tp >> 8) & 0xFF;
-    const float radiusA = __ldg(&px[pa].radius), radiusB = __ldg(&px[pb].radius);
+    const float radiusA = pradius(pa), radiusB = pradius(pb);
     const float4 cA4 = pos4(bA), cB4 = pos4(bB);
     const float4 vA4 = vel4(bA), vB4 = vel4(bB);
     const float4 kA = bc4(bA), kB = bc4(bB);
@@ -1323,9 +1342,9 @@ struct Sim {
           bA = pbody(pa);
           bB = pbody(pb);
           const int pc = (w & CI_PC_MASK) >> CI_PC_SHIFT;
-          const float fr = __ldg(&px[pa].friction) * __ldg(&px[pb].friction);
-          const float re = b2max(__ldg(&px[pa].restitution), __ldg(&px[pb].restitution));
-          const bool simple = pc == 1 && fr == 0.0f && re == 0.0f && __ldg(&px[pb].type) == SHAPE_CIRCLE;
+          // mixed friction sqrt(fA * fB) == 0 and mixed restitution max(rA, rB) == 0
+          const int fa = pflags(pa), fb = pflags(pb);
+          const bool simple = pc == 1 && ((fa | fb) & 4) != 0 && (fa & fb & 8) != 0 && (fb & 3) == SHAPE_CIRCLE;
           val = (uint32_t)i | ((uint32_t)bA << 16) | ((uint32_t)bB << 22) | (simple ? 0u : TL_GEN);
         }
       }
@@ -1448,22 +1467,10 @@ struct Sim {
       sweep4(b) = make_float4(p.x, p.y, p.z, 0.0f);
       oldq(b) = make_float2(x.z, x.w);
       float4 v = vel4(b);
-      // (SimplePhototaxisKilobot's linearDamping = 0, lib/kilobot.py:203, is folded into the template)
-      const float ld = __ldg(&bc[b].linearDamping);
-      const float ad = __ldg(&bc[b].angularDamping);
-      if (L.dampingMode == 0) {
-        const float fl = 1.0f / (1.0f + h * ld);
-        const float fa = 1.0f / (1.0f + h * ad);
-        v.x *= fl;
-        v.y *= fl;
-        v.z *= fa;
-      } else {
-        const float fl = b2clamp(1.0f - h * ld, 0.0f, 1.0f);
-        const float fa = b2clamp(1.0f - h * ad, 0.0f, 1.0f);
-        v.x *= fl;
-        v.y *= fl;
-        v.z *= fa;
-      }
+      const float2 df = damp(b);
+      v.x *= df.x;
+      v.y *= df.x;
+      v.z *= df.y;
       vel4(b) = v;
     }
     g.usync();
@@ -1629,9 +1636,9 @@ struct Sim {
   // shape AABB of proxy p under transform xf (b2Shape::ComputeAABB)
   __device__ __forceinline__ void shapeAABB(int p, Xf xf, V2* lo, V2* hi) {
     const ProxyConst* pc = px + p;
-    const int type = __ldg(&pc->type);
+    const int type = ptype(p);
     if (type == SHAPE_CIRCLE) {
-      const float r = __ldg(&pc->radius);
+      const float r = pradius(p);
       V2 c = xf.p + rmul(xf.q, mk(0.0f, 0.0f));
       *lo = mk(c.x - r, c.y - r);
       *hi = mk(c.x + r, c.y + r);
