@@ -571,7 +571,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   L.Pp = P;
   L.Cmax = round4(max_contacts > 0 ? max_contacts : std::min(P * (P - 1) / 2, 8 * B + 32));
   if (L.Cmax > 65535) L.Cmax = 65532;
-  L.Kmax = round4(std::min(std::min(L.Cmax, 3 * B + 16), (int)KB_MAX_SOLVER));
+  L.Kmax = round4(std::min(std::min(L.Cmax, 3 * B + 12), (int)KB_MAX_SOLVER));
   L.KW = round4((L.Kmax + 31) / 32);  // words per body mask over the touching list, padded to whole 128-bit loads
   {
     // general constraints can only arise between proxies that are not frictionless circles-with-zero-restitution
