@@ -147,3 +147,84 @@ def random_actions(scenario_or_dim, num_envs, steps, seed=1):
     A = scenario_or_dim if isinstance(scenario_or_dim, int) else scenario_or_dim.scenes[0].action_dim
     rng = np.random.Generator(np.random.Philox(key=seed))
     return rng.uniform(-0.01, 0.01, size=(steps, num_envs, A))
+
+
+# ----------------------------------------------------------------------------------------------
+# Extra parity scenes: they exercise the rest of the reference's hot-path surface (every object shape of
+# lib/body.py:288-334, object-object and object-table contacts, the other controllers and lights).
+def pushing_yard(num_envs=16, seed=0, env_offset=0, kilobot_kind=abi.KB_KILOBOT_SIMPLE_PHOTOTAXIS, num_kilobots=12,
+                 light="momentum", **scene_kw):
+    """A small 1.0 x 0.5 m arena (QuadPushingEnv's size, kilobots_test_envs.py:12) crowded with one object of
+    every shape and a swarm that follows a moving light: objects are pushed into each other and into the table."""
+    world = (1.0, 0.5)
+    objs = [S.quad_body(.1, .1), S.polygon_body(S.TFORM_TEMPLATE, .12, .12), S.polygon_body(S.CFORM_TEMPLATE, .12, .12),
+            S.polygon_body(S.LFORM_TEMPLATE, .12, .12), S.polygon_body(S.TRIANGLE_TEMPLATE, .12, .12), S.circle_body(.04)]
+    wb = np.array([world[0] / 2, world[1] / 2])
+    bounds = (-wb * 1.1, wb * 1.1)
+    act = (np.array([-1, -1]) * .01, np.array([1, 1]) * .01)
+    if light == "momentum":
+        lights = [S.LightSpec(abi.KB_LIGHT_MOMENTUM, radius=.3, bounds=bounds, action_bounds=act, max_velocity=.01)]
+    elif light == "composite":
+        lights = [S.LightSpec(abi.KB_LIGHT_CIRCULAR, radius=.25, bounds=bounds, action_bounds=act),
+                  S.LightSpec(abi.KB_LIGHT_MOMENTUM, radius=.2, bounds=bounds, action_bounds=act, max_velocity=.01)]
+    elif light == "linear":
+        lights = [S.LightSpec(abi.KB_LIGHT_LINEAR, action_bounds=(np.array([-2 * np.pi, 0.]), np.array([2 * np.pi, 0.])))]
+    else:
+        lights = [S.LightSpec(abi.KB_LIGHT_CIRCULAR, radius=.3, bounds=bounds, action_bounds=act)]
+    sc = S.SceneSpec(bodies=objs + [S.kilobot_body(kilobot_kind) for _ in range(num_kilobots)], num_objects=len(objs),
+                     lights=lights, world_size=world, **scene_kw)
+    rngs = _rng_for(seed, range(env_offset, env_offset + num_envs))
+    M = len(objs)
+    pose = np.zeros((num_envs, M + num_kilobots, 3))
+    slots = np.array([(-.36, .13), (-.2, -.1), (-.03, .12), (.13, -.1), (.28, .1), (.4, -.12)])
+    for e, r in enumerate(rngs):
+        pose[e, :M, :2] = slots + r.uniform(-.015, .015, size=(M, 2))
+        pose[e, :M, 2] = r.uniform(-np.pi, np.pi, size=M)
+    centre = np.stack([r.uniform(-.3, .3, size=2) * np.array([1.0, .4]) for r in rngs])
+    pose[:, M:, :2] = _separated_gaussian(rngs, centre, 0.08, num_kilobots, -wb + 0.02, wb - 0.02,
+                                          2 * S.KILOBOT_RADIUS + 1e-3)
+    for e, r in enumerate(rngs):
+        pose[e, M:, 2] = r.uniform(-np.pi, np.pi, size=num_kilobots)
+    ls = []
+    for e, r in enumerate(rngs):
+        row = []
+        for l in lights:
+            if l.type == abi.KB_LIGHT_MOMENTUM:
+                row += list(centre[e]) + [0.0, 0.0]
+            elif l.type == abi.KB_LIGHT_LINEAR:
+                row += [float(r.uniform(-np.pi, np.pi))]
+            else:
+                row += list(centre[e] + r.uniform(-.05, .05, size=2))
+        ls.append(row)
+    return Scenario("yard-%s" % light, [sc], None, pose, np.asarray(ls, dtype=np.float64), max_contacts=176)
+
+
+def direct_control(num_envs=16, seed=0, env_offset=0, **scene_kw):
+    """DirectControlKilobotsEnv-style batch (envs/direct_control_kilobots_env.py): velocity- and
+    acceleration-controlled kilobots around a quad, actions [E, N, 2] routed to Kilobot.set_action."""
+    world = (1.0, 0.5)
+    kinds = [abi.KB_KILOBOT_VELOCITY, abi.KB_KILOBOT_ACCELERATION] * 4
+    sc = S.SceneSpec(bodies=[S.quad_body(.1, .1), S.circle_body(.05)] + [S.kilobot_body(k) for k in kinds], num_objects=2,
+                     lights=[], world_size=world, **scene_kw)
+    rngs = _rng_for(seed, range(env_offset, env_offset + num_envs))
+    wb = np.array([world[0] / 2, world[1] / 2])
+    pose = np.zeros((num_envs, 2 + len(kinds), 3))
+    pose[:, 0, :2] = (-.12, 0.0)
+    pose[:, 1, :2] = (.12, 0.0)
+    ring = np.array([(np.cos(a), np.sin(a)) for a in np.linspace(0, 2 * np.pi, len(kinds), endpoint=False)]) * .2
+    ring[:, 1] *= .6
+    for e, r in enumerate(rngs):
+        pose[e, 2:, :2] = np.minimum(np.maximum(ring + r.uniform(-.01, .01, size=ring.shape), -wb + 0.02), wb - 0.02)
+        pose[e, 2:, 2] = r.uniform(-np.pi, np.pi, size=len(kinds))
+    return Scenario("direct", [sc], None, pose, np.zeros((num_envs, 0)), max_contacts=64)
+
+
+def random_kilobot_actions(scenario, num_envs, steps, seed=2):
+    """[steps, E, N, 2]: (v, omega) or (dv, domega) samples wide enough to hit the clips of
+    lib/kilobot.py:216-218,269."""
+    N = scenario.scenes[0].num_kilobots
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    a = np.zeros((steps, num_envs, N, 2))
+    a[..., 0] = rng.uniform(-0.004, 0.014, size=(steps, num_envs, N))
+    a[..., 1] = rng.uniform(-2.0, 2.0, size=(steps, num_envs, N))
+    return a.reshape(steps, num_envs, 2 * N)
