@@ -123,9 +123,16 @@ PROTOTYPES = {
     "get_mass_data": (C.c_int, [_VP, _VP]),
 }
 # exported by the product library only (the oracle has no state blob)
+class KbLaunchConfig(C.Structure):
+    _fields_ = [("lanes_per_env", C.c_int32), ("block_threads", C.c_int32), ("grid_blocks", C.c_int32),
+                ("smem_bytes_per_block", C.c_int32), ("state_words_per_env", C.c_int32),
+                ("smem_words_per_env", C.c_int32)]
+
+
 PRODUCT_ONLY = {
     "get_state": (C.c_int, [_VP, _VP]),
     "set_state": (C.c_int, [_VP, _VP]),
+    "get_launch_config": (C.c_int, [_VP, C.POINTER(KbLaunchConfig)]),
 }
 
 

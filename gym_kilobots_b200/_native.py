@@ -201,6 +201,11 @@ class NativeBatch:
         _check(_fn["get_mass_data"](self.h, _hptr(out)), "kb_get_mass_data")
         return out
 
+    def launch_config(self):
+        cfg = abi.KbLaunchConfig()
+        _check(_fn["get_launch_config"](self.h, C.byref(cfg)), "kb_get_launch_config")
+        return {k: int(getattr(cfg, k)) for k, _ in cfg._fields_}
+
     def get_state(self):
         out = np.zeros((self.E, self.state_bytes_per_env), np.uint8)
         _check(_fn["get_state"](self.h, _hptr(out)), "kb_get_state")

@@ -1032,6 +1032,18 @@ int kb_get_profile(KbHandle* hh, unsigned long long* out) {
 }
 #endif
 
+int kb_get_launch_config(const KbHandle* hh, KbLaunchConfig* cfg) {
+  const Handle* h = reinterpret_cast<const Handle*>(hh);
+  if (!h || !cfg) return fail(KB_ERR_INVALID, "kb_get_launch_config: null");
+  cfg->lanes_per_env = h->L.lanesPerEnv;
+  cfg->block_threads = KB_BLOCK_OF(h->L.lanesPerEnv);
+  cfg->grid_blocks = launchGrid(h);
+  cfg->smem_bytes_per_block = (int32_t)h->smemBytes;
+  cfg->state_words_per_env = h->L.stateWords;
+  cfg->smem_words_per_env = h->L.smemWords;
+  return KB_OK;
+}
+
 int kb_get_mass_data(KbHandle* hh, float* out) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h || !out) return fail(KB_ERR_INVALID, "kb_get_mass_data: null");

@@ -1498,10 +1498,12 @@ struct Sim {
       uint32_t item = k < nOrd ? ent(k) : IT_NONE;
       for (int r = 0; r < nRowsU; ++r) {
         if (IT_ROW(item) == r) {
-          if ((item & IT_GEN) != 0u) warmStartGeneralNI(*this, genSlot(k));
-          else warmStartSimple(k, item);
+          const uint32_t cur = item;
+          const int kc = k;
           k += LPE;
-          item = k < nOrd ? ent(k) : IT_NONE;
+          item = k < nOrd ? ent(k) : IT_NONE;  // next entry of this lane: fetched while the current one is solved
+          if ((cur & IT_GEN) != 0u) warmStartGeneralNI(*this, genSlot(kc));
+          else warmStartSimple(kc, cur);
         }
         g.usync();
       }
@@ -1511,10 +1513,12 @@ struct Sim {
       uint32_t item = k < nOrd ? ent(k) : IT_NONE;
       for (int r = 0; r < nRowsU; ++r) {
         if (IT_ROW(item) == r) {
-          if ((item & IT_GEN) != 0u) solveVelocityGeneralNI(*this, genSlot(k));
-          else solveVelocitySimple(k, item);
+          const uint32_t cur = item;
+          const int kc = k;
           k += LPE;
           item = k < nOrd ? ent(k) : IT_NONE;
+          if ((cur & IT_GEN) != 0u) solveVelocityGeneralNI(*this, genSlot(kc));
+          else solveVelocitySimple(kc, cur);
         }
         g.usync();
       }
@@ -1546,45 +1550,41 @@ struct Sim {
       pos4(b) = p;
       vel4(b) = v;
     }
-    for (int i = g.lane; i < nIslands; i += LPE) islflag(i) = 0u;  // bit0: unsolved this iteration, bit1: solved
     g.usync();
     KB_T(6);
-    // ---- position iterations with per-island early exit
+    // ---- position iterations with per-island early exit (b2Island::Solve breaks out of the loop of an island as
+    //      soon as one sweep leaves every separation above -3 linearSlop).  `unsolved` (one bit per island,
+    //      identical in every lane) is the set of islands still iterating.
     {
-      int remaining = nIslands;
+      unsigned long long unsolved = nIslands >= 64 ? ~0ull : ((1ull << nIslands) - 1ull);
       for (int it = 0; it < L.posIters; ++it) {
-        if (!g.uany(remaining > 0)) break;
-        nPit += (uint32_t)remaining;
+        if (!g.uany(unsolved != 0ull)) break;
+        nPit += (uint32_t)__popcll(unsolved);
+        unsigned long long bad = 0ull;  // islands with a constraint of this lane below the limit in this sweep
         int k = g.lane;
         uint32_t item = k < nOrd ? ent(k) : IT_NONE;
         for (int r = 0; r < nRowsU; ++r) {
           if (IT_ROW(item) == r) {
-            const int island = IT_ISL(item);
-            if ((islflag(island) & 2u) == 0u) {
-              const bool ok = (item & IT_GEN) != 0u ? solvePositionGeneralNI(*this, genSlot(k))
-                                                    : solvePositionSimple(k, item);
-              if (!ok) islflag(island).atomOr(1u);
-            }
+            const uint32_t cur = item;
+            const int kc = k;
             k += LPE;
             item = k < nOrd ? ent(k) : IT_NONE;
+            const int island = IT_ISL(cur);
+            if (((unsolved >> island) & 1ull) != 0ull) {
+              const bool ok = (cur & IT_GEN) != 0u ? solvePositionGeneralNI(*this, genSlot(kc))
+                                                   : solvePositionSimple(kc, cur);
+              if (!ok) bad |= 1ull << island;
+            }
           }
           g.usync();
         }
-        int solvedNow = 0;
-        for (int i = g.lane; i < nIslands; i += LPE) {
-          const uint32_t f = islflag(i);
-          if ((f & 2u) == 0u) {
-            if ((f & 1u) == 0u) {
-              islflag(i) = 2u;
-              ++solvedNow;
-            } else {
-              islflag(i) = 0u;
-            }
-          }
-        }
-        remaining -= (int)g.red_add((uint32_t)solvedNow);
-        g.usync();
+        const unsigned long long badAll = (unsigned long long)g.red_or((uint32_t)bad) |
+                                          ((unsigned long long)g.red_or((uint32_t)(bad >> 32)) << 32);
+        unsolved &= badAll;
       }
+      // bit 1: positionSolved (sleep bookkeeping below adds bit 2: minSleepTime < timeToSleep)
+      for (int i = g.lane; i < nIslands; i += LPE) islflag(i) = ((unsolved >> i) & 1ull) != 0ull ? 0u : 2u;
+      g.usync();
     }
     KB_T(7);
     // ---- copy back: SynchronizeTransform; sleep bookkeeping

@@ -213,6 +213,14 @@ int kb_get_controllers(KbHandle* h, double* ctrl, double* light);
 /* full per-env state blob (checkpoint / bit-exact resume): state_bytes_per_env * E bytes */
 int kb_get_state(KbHandle* h, void* out);
 int kb_set_state(KbHandle* h, const void* in);
+/* launch geometry of kb_step for this batch (reporting only): lanes of a warp that cooperate on one env
+   (4, 8, 16 or 32), threads per block, blocks in the grid, dynamic shared memory per block in bytes */
+typedef struct KbLaunchConfig {
+  int32_t lanes_per_env, block_threads, grid_blocks, smem_bytes_per_block;
+  int32_t state_words_per_env;   /* 32-bit words of per-env state resident in shared memory during a launch */
+  int32_t smem_words_per_env;    /* state + solver scratch */
+} KbLaunchConfig;
+int kb_get_launch_config(const KbHandle* h, KbLaunchConfig* cfg);
 /* derived mass data per scene: f32[num_scenes,B,4] = invMass invI localCenter.x localCenter.y */
 int kb_get_mass_data(KbHandle* h, float* out);
 
