@@ -641,7 +641,10 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   L.sTl = o;
   L.sOrd = o + L.Kmax;
   L.sLvlTab = o + 2 * L.Kmax;
-  o += std::max(std::max(8 * L.Kmax, 2 * L.Kmax + round4(L.Kmax + 2)), 2 * L.Pp);
+  // (outside solve() the region also holds the TOI alpha cache at 3*Kmax+8 and, after it, general records)
+  L.recWords = round4(std::max(std::max(std::max(8 * L.Kmax, 2 * L.Kmax + round4(L.Kmax + 2)), 2 * L.Pp),
+                               3 * L.Kmax + 8 + L.Cmax + 2 * GR_WORDS));
+  o += L.recWords;
   L.sMisc = o; o += 8;
   L.smemWords = round4(o);
   L.stepsPerAction = s0.steps_per_action;

@@ -115,6 +115,7 @@ struct Sim {
   int S;                        // index of the static table in the body arrays (== L.B)
   // per-launch counter increments (lane 0's copy is flushed to the blob at the end)
   uint32_t nSub, nCon, nPts, nLvl, nPit, nToi, nTests, nIsl;
+  float* genBase;               // where the general-constraint records of the current solve live
 #ifdef KB_PROFILE
   long long tp[KB_PROF_SLOTS], tlast;
   unsigned long long* profOut;   // this env's row of the profile buffer (TOI internals add to slots 13..15 directly)
@@ -122,6 +123,7 @@ struct Sim {
 
   __device__ __forceinline__ Sim(const Layout& l) : L(l) {
     nSub = nCon = nPts = nLvl = nPit = nToi = nTests = nIsl = 0u;
+    genBase = nullptr;
 #ifdef KB_PROFILE
     for (int i = 0; i < KB_PROF_SLOTS; ++i) tp[i] = 0;
     tlast = clock64();
@@ -170,10 +172,17 @@ struct Sim {
   // ---- HBM/L2-resident parts of the blob
   __device__ __forceinline__ double* ctrl(int k) { return reinterpret_cast<double*>(blob + L.oCtrl) + 4 * k; }
   __device__ __forceinline__ float* manifoldRec(int i) { return blob + L.oMan + MR_WORDS * i; }
-  __device__ __forceinline__ float* toiCache() { return blob + L.oToi; }
-  __device__ __forceinline__ float& pool(int f, int q) { return blob[L.oGen + GR_WORDS * q + f]; }
-  __device__ __forceinline__ uint32_t& poolu(int f, int q) { return reinterpret_cast<uint32_t*>(blob)[L.oGen + GR_WORDS * q + f]; }
-  __device__ __forceinline__ float& gw(int q, int w) { return blob[L.oGen + GR_WORDS * q + w]; }
+  // cached TOI alpha per contact (b2Contact::m_toi): lives in the record region, which is free outside solve()
+  __device__ __forceinline__ SU32 toiAlpha(int i) const { return SU32{wa(L.sRec + 3 * L.Kmax + 8 + i)}; }
+  // general-constraint records: in the free part of the shared-memory record region when they fit (they almost
+  // always do), else in the blob (HBM/L2).  genBase is a generic pointer either way; the records are only ever
+  // touched by the one lane that owns them.
+  __device__ __forceinline__ float* smemGeneric(int word) const {
+    return reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)wa(word)));
+  }
+  __device__ __forceinline__ float& pool(int f, int q) { return genBase[GR_WORDS * q + f]; }
+  __device__ __forceinline__ uint32_t& poolu(int f, int q) { return reinterpret_cast<uint32_t*>(genBase)[GR_WORDS * q + f]; }
+  __device__ __forceinline__ float& gw(int q, int w) { return genBase[GR_WORDS * q + w]; }
 
   __device__ __forceinline__ Xf bodyXf(int b) {
     float4 x = xf4(b);
@@ -1451,10 +1460,15 @@ struct Sim {
       misc(1) = (uint32_t)row;
       misc(2) = (uint32_t)nIslands;
       misc(3) = (uint32_t)maxL;
+      misc(4) = (uint32_t)nGen;
     }
     g.usync();
     const int nOrd = (int)misc(0), nRows = (int)misc(1), nIslands = (int)misc(2);
     const int nRowsU = g.umax(nRows);  // warp-uniform row count: the groups of a warp sweep their rows in lock step
+    {
+      const int nGen = (int)misc(4);
+      genBase = (8 * nOrd + GR_WORDS * nGen <= L.recWords) ? smemGeneric(L.sRec + 8 * nOrd) : blob + L.oGen;
+    }
     KB_T(3);
     nIsl += (uint32_t)nIslands;
     nLvl += misc(3);

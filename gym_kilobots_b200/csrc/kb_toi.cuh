@@ -482,13 +482,12 @@ __device__ __noinline__ uint32_t solveTOINI(Sim<LPE, UNI> s) {
 template <int LPE, bool UNI>
 __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
   const int B = L.B;
-  float* toi = toiCache();  // cached alpha per contact (HBM/L2; only touched when a table contact exists)
   int nC = (int)hdr(H_NC);
 
   for (int b = g.lane; b <= B; b += LPE) sweep4(b).set(3, 0.0f);  // alpha0 = 0
   for (int i = g.lane; i < nC; i += LPE) {
     cw(i) &= ~(CI_TOI | CI_TOICOUNT_MASK);
-    toi[i] = 1.0f;
+    toiAlpha(i) = f2u(1.0f);
   }
   g.sync();
 
@@ -553,7 +552,7 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
                               : time_of_impact(px + pa, sA, px + pb, sB);
           if (t >= 0.0f) alpha = b2min(alpha0 + (1.0f - alpha0) * t, 1.0f);
         }
-        toi[i] = alpha;
+        toiAlpha(i) = f2u(alpha);
         cw(i) |= CI_TOI;
       }
       g.sync();
@@ -571,7 +570,7 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
         const uint32_t w = cw(i);
         const int toiCount = (w & CI_TOICOUNT_MASK) >> CI_TOICOUNT_SHIFT;
         if ((w & CI_ENABLED) != 0u && toiCount <= KB_MAX_SUB_STEPS && (w & CI_TOI) != 0u) {
-          const float alpha = toi[i];
+          const float alpha = u2f(toiAlpha(i));
           if (alpha < 1.0f) {
             const uint32_t bits = f2u(alpha);
             if (bits < bestBits || (bits == bestBits && i > bestIdx)) {
@@ -637,6 +636,11 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
     // ---- mini island: minContact first, then the body's other touching wall contacts in list order
     //      (each re-evaluated at the advanced pose)
     const int islandCap = min(KB_MAX_TOI_CONTACTS, min(L.Gmax, L.Kmax));
+    {
+      // records of the mini island: behind the TOI cache in the record region if they fit, else in the blob
+      const int first = 3 * L.Kmax + 8 + L.Cmax;
+      genBase = (first + GR_WORDS * islandCap <= L.recWords) ? smemGeneric(L.sRec + first) : blob + L.oGen;
+    }
     int nIsland = 1;
     if (g.lane == 0) ord(0) = (uint32_t)minContact;
     for (int base = 0; base < nC; base += LPE) {
@@ -719,7 +723,7 @@ __device__ __forceinline__ void Sim<LPE, UNI>::solveTOI() {
     const int before = (int)hdr(H_NC);
     findNewContacts();
     const int after = (int)hdr(H_NC);
-    for (int i = before + g.lane; i < after; i += LPE) toi[i] = 1.0f;
+    for (int i = before + g.lane; i < after; i += LPE) toiAlpha(i) = f2u(1.0f);
     g.sync();
 #ifdef KB_PROFILE
     if (profOut && g.lane == 0) profOut[14] += (unsigned long long)(clock64() - tq0);   // event handling
