@@ -207,13 +207,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # clocks / throttle reasons are sampled from the first warm-up step to the end of the end-to-end leg (the
+    # timed region of a default run is only ~25 ms, shorter than nvidia-smi's sampling period)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # ---------------- device-resident leg
     for t in range(args.warmup):
         env.step_device(acts_d[t])
     cnt0 = b.counters().astype(np.float64).sum(0)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     wall0 = time.perf_counter()
@@ -224,7 +226,6 @@ def run_ours(args):
         ends[i].record()
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
     elapsed = float(step_ms.sum()) * 1e-3
     cnt1 = b.counters().astype(np.float64).sum(0)
@@ -240,6 +241,13 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     e2e_elapsed = time.perf_counter() - e0
     h2d, d2h = env.host_io_bytes()
+    # keep the GPU under the same load (untimed) until the sampler has seen it for at least ~0.6 s
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.6:
+        for _ in range(20):
+            env.step_device(acts_d[args.warmup])
+        torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
 
     if world > 1:
         t = torch.tensor([elapsed, e2e_elapsed], dtype=torch.float64, device=dev)
