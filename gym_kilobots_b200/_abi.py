@@ -133,6 +133,7 @@ PRODUCT_ONLY = {
     "get_state": (C.c_int, [_VP, _VP]),
     "set_state": (C.c_int, [_VP, _VP]),
     "get_launch_config": (C.c_int, [_VP, C.POINTER(KbLaunchConfig)]),
+    "get_host_layout": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 
 

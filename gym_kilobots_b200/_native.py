@@ -201,6 +201,13 @@ class NativeBatch:
         _check(_fn["get_mass_data"](self.h, _hptr(out)), "kb_get_mass_data")
         return out
 
+    def host_layout(self):
+        """(offsets of kilobots, objects, light, reward, status, done; total bytes) of the packed host block."""
+        off = (C.c_int64 * 6)()
+        total = C.c_int64()
+        _check(_fn["get_host_layout"](self.h, off, C.byref(total)), "kb_get_host_layout")
+        return [int(x) for x in off], int(total.value)
+
     def launch_config(self):
         cfg = abi.KbLaunchConfig()
         _check(_fn["get_launch_config"](self.h, C.byref(cfg)), "kb_get_launch_config")

@@ -220,6 +220,9 @@ struct Handle {
   LightConst* dLights = nullptr;
   // staging for kb_step_host
   double* dAction = nullptr;
+  // kb_step_host staging: ONE device allocation, sections at hostOff[] (see kb_get_host_layout)
+  uint8_t* dOut = nullptr;
+  int64_t hostOff[6] = {0, 0, 0, 0, 0, 0}, hostTotal = 0;
   float *dObsK = nullptr, *dObsO = nullptr, *dReward = nullptr;
   double* dObsL = nullptr;
   uint8_t* dDone = nullptr;
@@ -735,12 +738,24 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   CUDA_TRY(cudaMemset(h->dBlobs, 0, blobBytes));
   const int Amax = std::max(std::max(L.A, 2 * N), 1);
   CUDA_TRY(cudaMalloc(&h->dAction, sizeof(double) * (size_t)num_envs * Amax));
-  CUDA_TRY(cudaMalloc(&h->dObsK, sizeof(float) * (size_t)num_envs * std::max(N, 1) * 3));
-  CUDA_TRY(cudaMalloc(&h->dObsO, sizeof(float) * (size_t)num_envs * std::max(M, 1) * 3));
-  CUDA_TRY(cudaMalloc(&h->dObsL, sizeof(double) * (size_t)num_envs * std::max(L.L, 1)));
-  CUDA_TRY(cudaMalloc(&h->dReward, sizeof(float) * num_envs));
-  CUDA_TRY(cudaMalloc(&h->dDone, num_envs));
-  CUDA_TRY(cudaMalloc(&h->dStatus, sizeof(int32_t) * num_envs));
+  {
+    const int64_t sizes[6] = {(int64_t)sizeof(float) * num_envs * N * 3, (int64_t)sizeof(float) * num_envs * M * 3,
+                              (int64_t)sizeof(double) * num_envs * L.L, (int64_t)sizeof(float) * num_envs,
+                              (int64_t)sizeof(int32_t) * num_envs, (int64_t)num_envs};
+    int64_t off = 0;
+    for (int i = 0; i < 6; ++i) {
+      h->hostOff[i] = off;
+      off += (sizes[i] + 255) & ~(int64_t)255;
+    }
+    h->hostTotal = off;
+    CUDA_TRY(cudaMalloc(&h->dOut, (size_t)off + 256));
+    h->dObsK = reinterpret_cast<float*>(h->dOut + h->hostOff[0]);
+    h->dObsO = reinterpret_cast<float*>(h->dOut + h->hostOff[1]);
+    h->dObsL = reinterpret_cast<double*>(h->dOut + h->hostOff[2]);
+    h->dReward = reinterpret_cast<float*>(h->dOut + h->hostOff[3]);
+    h->dStatus = reinterpret_cast<int32_t*>(h->dOut + h->hostOff[4]);
+    h->dDone = h->dOut + h->hostOff[5];
+  }
 #ifdef KB_PROFILE
   CUDA_TRY(cudaMalloc(&h->dProf, sizeof(unsigned long long) * KB_PROF_SLOTS * (size_t)num_envs));
 #endif
@@ -766,8 +781,7 @@ int kb_destroy(KbHandle* hh) {
   if (!h) return KB_OK;
   cudaSetDevice(h->device);
   cudaFree(h->dBlobs); cudaFree(h->dEnvScene); cudaFree(h->dProxies); cudaFree(h->dBodies);
-  cudaFree(h->dScenes); cudaFree(h->dLights); cudaFree(h->dAction); cudaFree(h->dObsK); cudaFree(h->dObsO);
-  cudaFree(h->dObsL); cudaFree(h->dReward); cudaFree(h->dDone); cudaFree(h->dStatus);
+  cudaFree(h->dScenes); cudaFree(h->dLights); cudaFree(h->dAction); cudaFree(h->dOut);
   delete h;
   return KB_OK;
 }
@@ -853,6 +867,21 @@ int kb_step_host(KbHandle* hh, const double* action, int32_t action_mode, float*
                    obs_light ? h->dObsL : nullptr, reward ? h->dReward : nullptr, done ? h->dDone : nullptr,
                    status ? h->dStatus : nullptr, stream);
   if (rc != KB_OK) return rc;
+  {
+    // one device->host copy when the caller's buffers are laid out like the staging area (kb_get_host_layout)
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(obs_kilobots);
+    const bool packed = obs_kilobots && obs_objects && obs_light && reward && done && status &&
+                        reinterpret_cast<const uint8_t*>(obs_objects) == base + h->hostOff[1] &&
+                        reinterpret_cast<const uint8_t*>(obs_light) == base + h->hostOff[2] &&
+                        reinterpret_cast<const uint8_t*>(reward) == base + h->hostOff[3] &&
+                        reinterpret_cast<const uint8_t*>(status) == base + h->hostOff[4] &&
+                        reinterpret_cast<const uint8_t*>(done) == base + h->hostOff[5];
+    if (packed) {
+      CUDA_TRY(cudaMemcpyAsync(obs_kilobots, h->dOut, (size_t)h->hostTotal, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      return KB_OK;
+    }
+  }
   if (obs_kilobots) CUDA_TRY(cudaMemcpyAsync(obs_kilobots, h->dObsK, sizeof(float) * E * L.N * 3, cudaMemcpyDeviceToHost, st));
   if (obs_objects && L.M > 0) CUDA_TRY(cudaMemcpyAsync(obs_objects, h->dObsO, sizeof(float) * E * L.M * 3, cudaMemcpyDeviceToHost, st));
   if (obs_light && L.L > 0) CUDA_TRY(cudaMemcpyAsync(obs_light, h->dObsL, sizeof(double) * E * L.L, cudaMemcpyDeviceToHost, st));
@@ -1034,6 +1063,14 @@ int kb_get_profile(KbHandle* hh, unsigned long long* out) {
   return KB_OK;
 }
 #endif
+
+int kb_get_host_layout(const KbHandle* hh, int64_t* offsets, int64_t* total) {
+  const Handle* h = reinterpret_cast<const Handle*>(hh);
+  if (!h || !offsets || !total) return fail(KB_ERR_INVALID, "kb_get_host_layout: null");
+  for (int i = 0; i < 6; ++i) offsets[i] = h->hostOff[i];
+  *total = h->hostTotal;
+  return KB_OK;
+}
 
 int kb_get_launch_config(const KbHandle* hh, KbLaunchConfig* cfg) {
   const Handle* h = reinterpret_cast<const Handle*>(hh);

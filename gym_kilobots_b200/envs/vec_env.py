@@ -60,14 +60,22 @@ class KilobotsVecEnv:
             import torch
             b = self.batch
             pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
+            # one pinned block laid out like the library's staging area -> a single device->host copy per step
+            off, total = b.host_layout()
+            block = pin((max(total, 1),), torch.uint8)
+            self._host_block = block
+
+            def view(i, shape, dt):
+                n = int(np.prod(shape)) * np.dtype(dt).itemsize
+                return block[off[i]:off[i] + n].view(dt).reshape(shape)
             self._host = {
                 "action": pin((b.E, max(self.action_dim, 1)), torch.float64),
-                "kilobots": pin((b.E, b.N, 3), torch.float32),
-                "objects": pin((b.E, b.M, 3), torch.float32),
-                "light": pin((b.E, b.L), torch.float64),
-                "reward": pin((b.E,), torch.float32),
-                "done": pin((b.E,), torch.uint8),
-                "status": pin((b.E,), torch.int32),
+                "kilobots": view(0, (b.E, b.N, 3), np.float32),
+                "objects": view(1, (b.E, b.M, 3), np.float32),
+                "light": view(2, (b.E, b.L), np.float64),
+                "reward": view(3, (b.E,), np.float32),
+                "status": view(4, (b.E,), np.int32),
+                "done": view(5, (b.E,), np.uint8),
             }
         return self._host
 

@@ -213,6 +213,10 @@ int kb_get_controllers(KbHandle* h, double* ctrl, double* light);
 /* full per-env state blob (checkpoint / bit-exact resume): state_bytes_per_env * E bytes */
 int kb_get_state(KbHandle* h, void* out);
 int kb_set_state(KbHandle* h, const void* in);
+/* kb_step_host moves its six outputs with ONE device->host copy if the caller's buffers form one block laid out
+   like the library's staging area: byte offsets of (obs_kilobots, obs_objects, obs_light, reward, status, done)
+   from the start of that block, and its total size.  Any other arrangement of buffers works too (six copies). */
+int kb_get_host_layout(const KbHandle* h, int64_t offsets[6], int64_t* total_bytes);
 /* launch geometry of kb_step for this batch (reporting only): lanes of a warp that cooperate on one env
    (4, 8, 16 or 32), threads per block, blocks in the grid, dynamic shared memory per block in bytes */
 typedef struct KbLaunchConfig {

@@ -114,3 +114,25 @@ def test_full_size_c2_properties(oracle, native):
     kb = outs[-1]["kilobots"]
     assert np.isfinite(kb).all()
     assert (np.abs(kb[..., 0]) < 1.0 + 0.02).all() and (kb[..., 1] > -0.75 - 0.02).all()
+
+
+def test_vec_env_host_and_device_paths_agree(oracle, native):
+    """KilobotsVecEnv.step (host numpy, packed single D2H copy) == step_device (CUDA tensors) == oracle."""
+    import torch
+    from gym_kilobots_b200.envs import KilobotsVecEnv
+    sc = SC.c2_quad_assembly(37, degenerate=False)
+    acts = SC.random_actions(sc, sc.num_envs, 5)
+    ea, eb = KilobotsVecEnv(sc), KilobotsVecEnv(sc)
+    ob = oracle.OracleBatch(sc.scenes, sc.num_envs, sc.env_scene, sc.max_contacts, threads=8)
+    ea.reset(); eb.reset(); ob.reset(sc.body_pose, sc.light_state)
+    for t in range(5):
+        obs_h, rew_h, done_h, info_h = ea.step(acts[t])
+        obs_d, rew_d, done_d, info_d = eb.step_device(torch.as_tensor(acts[t], device="cuda"))
+        oo = ob.step(acts[t])
+        for k in ("kilobots", "objects", "light"):
+            assert np.array_equal(obs_h[k], obs_d[k].cpu().numpy()), (t, k)
+            assert np.array_equal(obs_h[k], oo[k]), (t, k)
+        assert np.array_equal(rew_h, rew_d.cpu().numpy()) and np.array_equal(rew_h, oo["reward"])
+        assert not done_h.any() and not info_h["status"].any()
+    h2d, d2h = ea.host_io_bytes()
+    assert h2d == 37 * 2 * 8 and d2h == 37 * (15 * 12 + 4 * 12 + 2 * 8 + 4 + 1 + 4)
