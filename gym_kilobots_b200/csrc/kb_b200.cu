@@ -23,16 +23,22 @@ namespace kb {
 
 // ----------------------------------------------------------------------------------- kernels
 // threads per block: two warps (one for 4-lane groups, whose 8 envs per warp already fill a block's shared memory)
+#ifndef KB_BLOCK4
+#define KB_BLOCK4 32
+#endif
 #ifndef KB_BLOCK8
 #define KB_BLOCK8 64
 #endif
-#define KB_BLOCK_OF(LPE) ((LPE) == 4 ? 32 : ((LPE) == 8 ? KB_BLOCK8 : 64))
+#ifndef KB_BLOCK16
+#define KB_BLOCK16 64
+#endif
+#define KB_BLOCK_OF(LPE) ((LPE) == 4 ? KB_BLOCK4 : ((LPE) == 8 ? KB_BLOCK8 : ((LPE) == 16 ? KB_BLOCK16 : 64)))
 
 // The batch is padded to a whole number of blocks (numEnvs <= grid * EPB): every lane of the step kernel owns
 // a real environment, so the groups of a warp can run in lock step.  Padding envs replicate the inputs of the
 // last real env and never write outputs.
 template <int LPE>
-__global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? 8 : (LPE == 16 ? 6 : (KB_BLOCK_OF(LPE) > 64 ? 1 : 3)))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? 8 : (KB_BLOCK_OF(LPE) > 64 ? 1 : (LPE == 16 ? 6 : 3)))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
   constexpr int EPB = KB_BLOCK_OF(LPE) / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;

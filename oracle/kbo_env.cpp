@@ -461,7 +461,8 @@ int kbo_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env
     maxP = std::max(maxP, p);
   }
   h->numProxies = maxP;
-  h->maxContacts = max_contacts > 0 ? max_contacts : 8 * h->numBodies + 32;
+  // same default and rounding as the product library (kb_create): min(P(P-1)/2, 8B+32), up to a multiple of 4
+  h->maxContacts = ((max_contacts > 0 ? max_contacts : std::min(maxP * (maxP - 1) / 2, 8 * h->numBodies + 32)) + 3) & ~3;
   ComputeMotorConstants(h, 1. / 10);
   h->envs.resize(num_envs);
   for (int i = 0; i < num_envs; ++i) h->envs[i].scene = env_scene ? env_scene[i] : 0;
