@@ -136,3 +136,76 @@ def test_vec_env_host_and_device_paths_agree(oracle, native):
         assert not done_h.any() and not info_h["status"].any()
     h2d, d2h = ea.host_io_bytes()
     assert h2d == 37 * 2 * 8 and d2h == 37 * (15 * 12 + 4 * 12 + 2 * 8 + 4 + 1 + 4)
+
+
+def _oracle_backed(cls, oracle):
+    class Injected(cls):
+        def _make_batch(self, spec):
+            return oracle.OracleBatch(spec, 1)
+    return Injected
+
+
+def test_single_env_facades_on_the_gpu_match_the_oracle(oracle, native):
+    """The E = 1 drop-in classes (gym_kilobots.envs.*) stepping on the B200 vs. the same classes on the oracle."""
+    import yaml
+    from gym_kilobots_b200.envs import (DirectControlKilobotsEnv, QuadAssemblyKilobotsEnv, YamlKilobotsEnv)
+    from gym_kilobots_b200.lib import Quad, SimpleVelocityControlKilobot
+
+    def same(a, b, what):
+        for k in ("kilobots", "objects", "light"):
+            assert np.array_equal(a[k], b[k]), (what, k)
+
+    # QuadAssemblyKilobotsEnv (kilobots_test_envs.py:23-95)
+    eg, eo = QuadAssemblyKilobotsEnv(seed=7), _oracle_backed(QuadAssemblyKilobotsEnv, oracle)(seed=7)
+    same(eg.reset(), eo.reset(), "quad assembly reset")
+    rng = np.random.default_rng(0)
+    for t in range(6):
+        a = rng.uniform(-.01, .01, size=2)
+        og, rg, dg, ig = eg.step(a)
+        oo, ro, do, io = eo.step(a)
+        same(og, oo, "quad assembly step %d" % t)
+        assert rg == ro == 1.0 and dg is False and ig is None
+    assert np.array_equal(eg.kilobots[3].get_pose(), eo.kilobots[3].get_pose())
+
+    # YamlKilobotsEnv (yaml_kilobots_env.py:101-369)
+    text = """
+!EvalEnv
+width: 1.0
+height: 1.0
+resolution: 600
+objects:
+  - !ObjectConf {idx: 0, color: null, shape: l_shape, width: .15, height: .15, init: [.1, -.1, .3], symmetry: null}
+  - !ObjectConf {idx: 1, color: null, shape: circle, width: .05, height: .05, init: [.2, .2, 0.], symmetry: null}
+light: !LightConf {type: momentum, init: [0., 0.], radius: .2}
+kilobots: !KilobotsConf {num: 7, mean: [0., 0.], std: .03}
+"""
+    conf = yaml.load(text, Loader=yaml.Loader)
+    import random
+
+    def seeded(cls):
+        np.random.seed(3)
+        random.seed(3)
+        e = cls(configuration=conf)
+        return e, e.reset()
+    eg, og0 = seeded(YamlKilobotsEnv)
+    eo, oo0 = seeded(_oracle_backed(YamlKilobotsEnv, oracle))
+    same(og0, oo0, "yaml reset")
+    for t in range(4):
+        a = rng.uniform(-.01, .01, size=2)
+        same(eg.step(a)[0], eo.step(a)[0], "yaml step %d" % t)
+
+    # DirectControlKilobotsEnv (direct_control_kilobots_env.py:8-29)
+    class Env(DirectControlKilobotsEnv):
+        def _configure_environment(self):
+            self._objects = [Quad(world=self.world, width=.1, height=.1, position=(.08, .0))]
+            self._kilobots = [SimpleVelocityControlKilobot(self.world, position=(-.04 * i, .0), orientation=.0,
+                                                           velocity=[.005, .0]) for i in range(3)]
+
+        def get_reward(self, *a):
+            return 0.
+
+    eg, eo = Env(), _oracle_backed(Env, oracle)()
+    same(eg.reset(), eo.reset(), "direct reset")
+    for t in range(6):
+        a = np.stack([rng.uniform(0, .012, size=3), rng.uniform(-1.8, 1.8, size=3)], axis=1)
+        same(eg.step(a)[0], eo.step(a)[0], "direct step %d" % t)
