@@ -90,7 +90,10 @@ extern __shared__ __align__(16) uint32_t kb_smem[];
 // alive and the boundaries sit in block-uniform control flow): the warps of a block then walk the same code at
 // the same time and share instruction-cache lines -- the instruction footprint of one sub-step is several times
 // the L1.5 instruction cache, and without this the fetch stalls were ~20 % of all warp stalls (profiles/).
-#define KB_T(i) do { if (UNI) __syncthreads(); } while (0)
+#ifndef KB_SYNC_PHASES
+#define KB_SYNC_PHASES 0xFFFu   /* bit i: rendezvous at phase boundary i */
+#endif
+#define KB_T(i) do { if (UNI && ((KB_SYNC_PHASES >> (i)) & 1u)) __syncthreads(); } while (0)
 #endif
 
 template <int LPE, bool UNI>
