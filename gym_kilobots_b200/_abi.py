@@ -24,6 +24,11 @@ KB_STATUS_CONTACT_OVERFLOW = 1
 KB_STATUS_NONFINITE = 2
 KB_STATUS_SOLVER_OVERFLOW = 4
 
+# task layer (extension beyond the reference, include/kb_b200.h "Task layer")
+KB_TASK_CONST, KB_TASK_OBJECT_TO_TARGET, KB_TASK_SWARM_TO_TARGET = 0, 1, 2
+KB_EPISODE_STATS = 6
+EPISODE_STAT_NAMES = ("return", "length", "position_error", "orientation_error", "success", "done_count")
+
 COUNTER_NAMES = ("substeps", "contacts", "points", "levels", "pos_iters", "toi_events", "pair_tests", "islands")
 
 
@@ -103,6 +108,21 @@ class KbDims(C.Structure):
     ]
 
 
+class KbTaskDef(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32),
+        ("object", C.c_int32),
+        ("max_episode_steps", C.c_int32),
+        ("reserved", C.c_int32),
+        ("w_position", C.c_double),
+        ("w_orientation", C.c_double),
+        ("step_penalty", C.c_double),
+        ("success_bonus", C.c_double),
+        ("position_tolerance", C.c_double),
+        ("orientation_tolerance", C.c_double),
+    ]
+
+
 # name -> (restype, argtypes); the exported symbol is prefix + name
 _VP = C.c_void_p
 PROTOTYPES = {
@@ -121,6 +141,10 @@ PROTOTYPES = {
     "get_proxies": (C.c_int, [_VP, _VP]),
     "get_controllers": (C.c_int, [_VP, _VP, _VP]),
     "get_mass_data": (C.c_int, [_VP, _VP]),
+    "set_task": (C.c_int, [_VP, C.POINTER(KbTaskDef), _VP]),
+    "get_episode_stats": (C.c_int, [_VP, _VP]),
+    "bind_flat_observation": (C.c_int, [_VP, _VP]),
+    "flat_observation_dim": (C.c_int, [_VP]),
 }
 # exported by the product library only (the oracle has no state blob)
 class KbLaunchConfig(C.Structure):

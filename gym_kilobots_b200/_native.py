@@ -201,6 +201,29 @@ class NativeBatch:
         _check(_fn["get_mass_data"](self.h, _hptr(out)), "kb_get_mass_data")
         return out
 
+    # ---- task layer (extension: on-device reward / done / episode statistics / flat observation)
+    def set_task(self, task, targets=None):
+        """task: scene.TaskSpec; targets: [E,3] (x m, y m, theta) or None to keep the current ones."""
+        t = task.to_def()
+        tg = None if targets is None else np.ascontiguousarray(targets, dtype=np.float64).reshape(self.E, 3)
+        _check(_fn["set_task"](self.h, C.byref(t), _hptr(tg)), "kb_set_task")
+
+    def episode_stats(self):
+        out = np.zeros((self.E, abi.KB_EPISODE_STATS), np.float64)
+        _check(_fn["get_episode_stats"](self.h, _hptr(out)), "kb_get_episode_stats")
+        return out
+
+    def bind_flat_observation(self, enable=True):
+        """Device tensor f32[E, 2N+L+4M] in YamlKilobotsEnv.observation_space order, refreshed by every step."""
+        if not enable:
+            self.obs_flat = None
+            _check(_fn["bind_flat_observation"](self.h, None), "kb_bind_flat_observation")
+            return None
+        dim = _fn["flat_observation_dim"](self.h)
+        self.obs_flat = self.torch.zeros((self.E, dim), dtype=self.torch.float32, device=self.device)
+        _check(_fn["bind_flat_observation"](self.h, C.c_void_p(self.obs_flat.data_ptr())), "kb_bind_flat_observation")
+        return self.obs_flat
+
     def host_layout(self):
         """(offsets of kilobots, objects, light, reward, status, done; total bytes) of the packed host block."""
         off = (C.c_int64 * 6)()

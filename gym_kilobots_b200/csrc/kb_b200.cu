@@ -32,13 +32,19 @@ namespace kb {
 #ifndef KB_BLOCK16
 #define KB_BLOCK16 64
 #endif
+#ifndef KB_MINBLOCKS16
+#define KB_MINBLOCKS16 6
+#endif
+#ifndef KB_MINBLOCKS8
+#define KB_MINBLOCKS8 3
+#endif
 #define KB_BLOCK_OF(LPE) ((LPE) == 4 ? KB_BLOCK4 : ((LPE) == 8 ? KB_BLOCK8 : ((LPE) == 16 ? KB_BLOCK16 : 64)))
 
 // The batch is padded to a whole number of blocks (numEnvs <= grid * EPB): every lane of the step kernel owns
 // a real environment, so the groups of a warp can run in lock step.  Padding envs replicate the inputs of the
 // last real env and never write outputs.
 template <int LPE>
-__global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? 8 : (KB_BLOCK_OF(LPE) > 64 ? 1 : (LPE == 16 ? 6 : 3)))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? 8 : (KB_BLOCK_OF(LPE) > 64 ? 1 : (LPE == 16 ? KB_MINBLOCKS16 : KB_MINBLOCKS8)))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
   constexpr int EPB = KB_BLOCK_OF(LPE) / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
@@ -62,6 +68,8 @@ __global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? 8 : (KB_BLOCK_O
   const double* act = a.action ? a.action + (size_t)envIn * A : nullptr;
   if (a.actionMode == KB_ACTION_KILOBOTS) s.setKilobotActions(act);
   s.g.usync();
+  if (a.task.mode != KB_TASK_CONST && s.g.lane == 0 && env < a.numEnvs)  // task layer, include/kb_b200.h
+    s.taskBegin(a.task, a.taskState + (size_t)env * KB_TASK_WORDS);
   for (int step = 0; step < a.L.stepsPerAction; ++step) {
     __syncthreads();  // keeps the warps of a block in the same phase (see KB_T in kb_step.cuh)
     if (a.actionMode == KB_ACTION_LIGHT && act && a.L.numLights > 0) s.lightStep(act);
@@ -103,6 +111,12 @@ __global__ void __launch_bounds__(KB_BLOCK_OF(LPE)) kb_reset_kernel(const __grid
     s.hdr(H_NC) = 0u;
     s.hdr(H_STATUS) = 0u;
     s.hdr(H_SCENE) = (uint32_t)scene;
+    if (a.taskState && env < a.numEnvs) {  // a new episode: return and length restart (task layer)
+      double* ts = a.taskState + (size_t)env * KB_TASK_WORDS;
+      ts[3 + KB_EP_RETURN] = 0.0;
+      ts[3 + KB_EP_LENGTH] = 0.0;
+      ts[3 + KB_EP_SUCCESS] = 0.0;
+    }
   }
   // light.__init__ / MomentumLight(velocity=...) / GradientLight(angle=...)
   if (a.lightInit)
@@ -233,6 +247,10 @@ struct Handle {
   double* dObsL = nullptr;
   uint8_t* dDone = nullptr;
   int32_t* dStatus = nullptr;
+  // task layer (extension)
+  TaskConst task = {};
+  double* dTask = nullptr;   // [E][KB_TASK_WORDS]
+  float* obsFlat = nullptr;  // caller-owned device buffer bound by kb_bind_flat_observation
   int envsPerBlock = 4;
   size_t smemBytes = 0;
 #ifdef KB_PROFILE
@@ -521,6 +539,8 @@ static void fillArgs(const Handle* h, KernelArgs* a) {
   a->scenes = h->dScenes;
   a->lights = h->dLights;
   a->numEnvs = h->numEnvs;
+  a->task = h->task;
+  a->taskState = h->dTask;
 #ifdef KB_PROFILE
   a->prof = h->dProf;
 #endif
@@ -762,6 +782,8 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     h->dStatus = reinterpret_cast<int32_t*>(h->dOut + h->hostOff[4]);
     h->dDone = h->dOut + h->hostOff[5];
   }
+  CUDA_TRY(cudaMalloc(&h->dTask, sizeof(double) * KB_TASK_WORDS * (size_t)num_envs));
+  CUDA_TRY(cudaMemset(h->dTask, 0, sizeof(double) * KB_TASK_WORDS * (size_t)num_envs));
 #ifdef KB_PROFILE
   CUDA_TRY(cudaMalloc(&h->dProf, sizeof(unsigned long long) * KB_PROF_SLOTS * (size_t)num_envs));
 #endif
@@ -787,7 +809,7 @@ int kb_destroy(KbHandle* hh) {
   if (!h) return KB_OK;
   cudaSetDevice(h->device);
   cudaFree(h->dBlobs); cudaFree(h->dEnvScene); cudaFree(h->dProxies); cudaFree(h->dBodies);
-  cudaFree(h->dScenes); cudaFree(h->dLights); cudaFree(h->dAction); cudaFree(h->dOut);
+  cudaFree(h->dScenes); cudaFree(h->dLights); cudaFree(h->dAction); cudaFree(h->dOut); cudaFree(h->dTask);
   delete h;
   return KB_OK;
 }
@@ -850,6 +872,7 @@ int kb_step(KbHandle* hh, const double* action, int32_t action_mode, float* obs_
   a.reward = reward;
   a.done = done;
   a.status = status;
+  a.obsFlat = h->obsFlat;
   KB_LAUNCH(kb_step_kernel, h, (cudaStream_t)stream, a);
   CUDA_TRY(cudaGetLastError());
   return KB_OK;
@@ -1088,6 +1111,68 @@ int kb_get_launch_config(const KbHandle* hh, KbLaunchConfig* cfg) {
   cfg->state_words_per_env = h->L.stateWords;
   cfg->smem_words_per_env = h->L.smemWords;
   return KB_OK;
+}
+
+// ---- task layer (extension beyond the reference; include/kb_b200.h "Task layer") -------------------------
+int kb_set_task(KbHandle* hh, const KbTaskDef* task, const double* target) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !task) return fail(KB_ERR_INVALID, "kb_set_task: null");
+  if (task->mode != KB_TASK_CONST && task->mode != KB_TASK_OBJECT_TO_TARGET && task->mode != KB_TASK_SWARM_TO_TARGET)
+    return fail(KB_ERR_INVALID, "kb_set_task: unknown mode");
+  if (task->mode == KB_TASK_OBJECT_TO_TARGET && (task->object < 0 || task->object >= h->L.M))
+    return fail(KB_ERR_INVALID, "kb_set_task: object index out of range");
+  if (task->mode == KB_TASK_SWARM_TO_TARGET && h->L.N < 1) return fail(KB_ERR_INVALID, "kb_set_task: no kilobots");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t E = (size_t)h->numEnvs;
+  std::vector<double> ts(E * KB_TASK_WORDS, 0.0);
+  if (!target) {  // keep the current targets
+    CUDA_TRY(cudaMemcpy(ts.data(), h->dTask, sizeof(double) * ts.size(), cudaMemcpyDeviceToHost));
+    for (size_t e = 0; e < E; ++e)
+      for (int k = 3; k < KB_TASK_WORDS; ++k) ts[e * KB_TASK_WORDS + k] = 0.0;
+  } else {
+    for (size_t e = 0; e < E; ++e)
+      for (int k = 0; k < 3; ++k) ts[e * KB_TASK_WORDS + k] = target[e * 3 + k];
+  }
+  CUDA_TRY(cudaMemcpy(h->dTask, ts.data(), sizeof(double) * ts.size(), cudaMemcpyHostToDevice));
+  TaskConst& t = h->task;
+  t.mode = task->mode;
+  t.object = task->object;
+  t.maxSteps = task->max_episode_steps;
+  t.pad = 0;
+  t.wPos = task->w_position;
+  t.wAng = task->w_orientation;
+  t.stepPenalty = task->step_penalty;
+  t.bonus = task->success_bonus;
+  t.posTol = task->position_tolerance;
+  t.angTol = task->orientation_tolerance;
+  return KB_OK;
+}
+
+int kb_get_episode_stats(KbHandle* hh, double* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !out) return fail(KB_ERR_INVALID, "kb_get_episode_stats: null");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t E = (size_t)h->numEnvs;
+  std::vector<double> ts(E * KB_TASK_WORDS);
+  CUDA_TRY(cudaMemcpy(ts.data(), h->dTask, sizeof(double) * ts.size(), cudaMemcpyDeviceToHost));
+  for (size_t e = 0; e < E; ++e)
+    for (int k = 0; k < KB_EPISODE_STATS; ++k) out[e * KB_EPISODE_STATS + k] = ts[e * KB_TASK_WORDS + 3 + k];
+  return KB_OK;
+}
+
+int kb_bind_flat_observation(KbHandle* hh, float* obs_flat) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(KB_ERR_INVALID, "kb_bind_flat_observation: null handle");
+  h->obsFlat = obs_flat;
+  return KB_OK;
+}
+
+int kb_flat_observation_dim(const KbHandle* hh) {
+  const Handle* h = reinterpret_cast<const Handle*>(hh);
+  if (!h) return fail(KB_ERR_INVALID, "kb_flat_observation_dim: null handle");
+  return 2 * h->L.N + h->L.L + 4 * h->L.M;
 }
 
 int kb_get_mass_data(KbHandle* hh, float* out) {

@@ -21,6 +21,14 @@
 
 namespace kb {
 
+// task layer (extension, include/kb_b200.h "Task layer"): constants of the handle's KbTaskDef
+struct TaskConst {
+  int32_t mode, object, maxSteps, pad;
+  double wPos, wAng, stepPenalty, bonus, posTol, angTol;
+};
+// per-env task words (float64): target x y theta, then the KB_EPISODE_STATS statistics
+#define KB_TASK_WORDS (3 + KB_EPISODE_STATS + 2)   /* + the task error at the start of the current env-step */
+
 struct KernelArgs {
   Layout L;
   float* blobs;                 // [E][blobWords]
@@ -39,6 +47,9 @@ struct KernelArgs {
   float* reward;
   uint8_t* done;
   int32_t* status;
+  TaskConst task;
+  double* taskState;            // [E][KB_TASK_WORDS]
+  float* obsFlat;               // [E][2N + L + 4M] or null
 #ifdef KB_PROFILE
   unsigned long long* prof;     // [E][KB_PROF_SLOTS] cycles per phase (debug builds only)
 #endif
@@ -1829,31 +1840,102 @@ struct Sim {
   __device__ __forceinline__ void solveTOI();   // kb_toi.cuh
 
   // ----------------------------------------------------------------------------- outputs
+  // task layer (extension): distance (m) and |angle| (rad) between the task's subject and its target, float64,
+  // sequential sums -- the oracle evaluates the same expressions in the same order (oracle/kbo_env.cpp TaskError)
+  __device__ __forceinline__ void taskError(const TaskConst& tk, const double* tgt, double* dist, double* ang) {
+    double px, py, th = 0.0;
+    if (tk.mode == KB_TASK_OBJECT_TO_TARGET) {
+      const float4 x = xf4(tk.object);
+      px = (double)x.x / 25.0;
+      py = (double)x.y / 25.0;
+      th = (double)pos4(tk.object).get(2);
+    } else {
+      double sx = 0.0, sy = 0.0;
+      for (int b = L.M; b < L.B; ++b) {
+        const float4 x = xf4(b);
+        sx += (double)x.x / 25.0;
+        sy += (double)x.y / 25.0;
+      }
+      px = sx / (double)L.N;
+      py = sy / (double)L.N;
+    }
+    const double dx = px - tgt[0], dy = py - tgt[1];
+    *dist = sqrt(dx * dx + dy * dy);
+    *ang = tk.mode == KB_TASK_OBJECT_TO_TARGET ? fabs(remainder(th - tgt[2], 6.283185307179586)) : 0.0;
+  }
+
+  // task error before the env-step, kept in the env's task words (not in registers) until gather
+  __device__ __forceinline__ void taskBegin(const TaskConst& tk, double* ts) {
+    double d0, a0;
+    taskError(tk, ts, &d0, &a0);
+    ts[3 + KB_EPISODE_STATS] = d0;
+    ts[3 + KB_EPISODE_STATS + 1] = a0;
+  }
+
+  // get_state (kilobots_env.py:115-118) + the reward / done / info hooks (:123-131)
   __device__ __forceinline__ void gather(const KernelArgs& a, int env) {
     g.sync();
     const int M = L.M, N = L.N;
     bool bad = false;
+    float* flat = a.obsFlat ? a.obsFlat + (size_t)env * (2 * N + L.L + 4 * M) : nullptr;
     for (int b = g.lane; b < L.B; b += LPE) {
       const float4 x = xf4(b);
       const float ang = pos4(b).get(2);
       bad |= !(isfinite(x.x) && isfinite(x.y) && isfinite(ang));
       float* o = b < M ? (a.obsObjects ? a.obsObjects + ((size_t)env * M + b) * 3 : nullptr)
                        : (a.obsKilobots ? a.obsKilobots + ((size_t)env * N + (b - M)) * 3 : nullptr);
+      const float ox = (float)((double)x.x / 25.0), oy = (float)((double)x.y / 25.0);
       if (o) {
-        o[0] = (float)((double)x.x / 25.0);
-        o[1] = (float)((double)x.y / 25.0);
+        o[0] = ox;
+        o[1] = oy;
         o[2] = ang;
+      }
+      if (flat) {
+        // YamlKilobotsEnv.observation_space layout (yaml_kilobots_env.py:163-178)
+        if (b < M) {
+          float* f = flat + 2 * N + L.L + 4 * b;
+          f[0] = ox; f[1] = oy; f[2] = x.z; f[3] = x.w;   // xf.q = (sin, cos) of the body angle
+        } else {
+          flat[2 * (b - M)] = ox;
+          flat[2 * (b - M) + 1] = oy;
+        }
       }
     }
     if (g.any(bad) && g.lane == 0) hdr(H_STATUS) |= KB_STATUS_NONFINITE;
-    if (a.obsLight) {
+    if (a.obsLight || flat) {
       const SF64Arr ls = lightState();
-      for (int i = g.lane; i < L.L; i += LPE) a.obsLight[(size_t)env * L.L + i] = ls[i];
+      for (int i = g.lane; i < L.L; i += LPE) {
+        const double v = ls[i];
+        if (a.obsLight) a.obsLight[(size_t)env * L.L + i] = v;
+        if (flat) flat[2 * N + i] = (float)v;
+      }
     }
     g.sync();
     if (g.lane == 0) {
-      if (a.reward) a.reward[env] = __ldg(&a.scenes[a.envScene ? a.envScene[env] : 0].rewardConst);
-      if (a.done) a.done[env] = 0;
+      float rew = __ldg(&a.scenes[a.envScene ? a.envScene[env] : 0].rewardConst);
+      uint8_t dn = 0;
+      if (a.task.mode != KB_TASK_CONST) {
+        double* ts = a.taskState + (size_t)env * KB_TASK_WORDS;
+        double d1, a1;
+        taskError(a.task, ts, &d1, &a1);
+        const double d0 = ts[3 + KB_EPISODE_STATS], a0 = ts[3 + KB_EPISODE_STATS + 1];  // stashed by taskBegin
+        const bool success = d1 <= a.task.posTol && a1 <= a.task.angTol;
+        double r = a.task.wPos * (d0 - d1);
+        r = r + a.task.wAng * (a0 - a1);
+        r = r - a.task.stepPenalty;
+        if (success) r = r + a.task.bonus;
+        const double len = ts[3 + KB_EP_LENGTH] + 1.0;
+        dn = (success || (a.task.maxSteps > 0 && len >= (double)a.task.maxSteps)) ? 1 : 0;
+        ts[3 + KB_EP_RETURN] += r;
+        ts[3 + KB_EP_LENGTH] = len;
+        ts[3 + KB_EP_POSITION_ERROR] = d1;
+        ts[3 + KB_EP_ORIENTATION_ERROR] = a1;
+        ts[3 + KB_EP_SUCCESS] = success ? 1.0 : 0.0;
+        if (dn) ts[3 + KB_EP_DONE_COUNT] += 1.0;
+        rew = (float)r;
+      }
+      if (a.reward) a.reward[env] = rew;
+      if (a.done) a.done[env] = dn;
       if (a.status) a.status[env] = (int32_t)hdr(H_STATUS);
     }
   }

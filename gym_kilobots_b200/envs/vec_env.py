@@ -18,7 +18,11 @@ class KilobotsVecEnv:
     with the attributes scenes / env_scene / body_pose / light_state / max_contacts.
     """
 
-    def __init__(self, scenario, device=0, action_mode=abi.KB_ACTION_LIGHT):
+    def __init__(self, scenario, device=0, action_mode=abi.KB_ACTION_LIGHT, task=None, targets=None,
+                 flat_observation=False):
+        """task / targets: optional `scene.TaskSpec` and per-env target poses [E,3] -- on-device reward, done and
+        episode statistics (an extension: the reference's hooks are abstract and its in-tree envs return constants).
+        flat_observation: also emit obs['flat'], the vector YamlKilobotsEnv.observation_space describes."""
         self.scenario = scenario
         self.batch = _native.NativeBatch(scenario.scenes, scenario.body_pose.shape[0], scenario.env_scene,
                                          scenario.max_contacts, device=device)
@@ -29,6 +33,24 @@ class KilobotsVecEnv:
         self.action_dim = 2 * self.batch.N if action_mode == abi.KB_ACTION_KILOBOTS else self.batch.A
         self._host = None
         self._sim_steps = 0
+        self.obs_flat = self.batch.bind_flat_observation() if flat_observation else None
+        if task is not None:
+            self.set_task(task, targets)
+
+    # -- task layer (extension) -----------------------------------------------------------------
+    def set_task(self, task, targets=None):
+        self.batch.set_task(task, targets)
+
+    def episode_stats(self):
+        """dict of [E] float64 arrays: return, length, position_error, orientation_error, success, done_count."""
+        st = self.batch.episode_stats()
+        return {n: st[:, i] for i, n in enumerate(abi.EPISODE_STAT_NAMES)}
+
+    def reset_done(self, done, body_pose=None, light_state=None):
+        """Auto-reset: rebuild only the envs whose `done` flag is set (device or host array)."""
+        pose = self.scenario.body_pose if body_pose is None else body_pose
+        light = self.scenario.light_state if light_state is None else light_state
+        self.batch.reset(pose, light, None, done)
 
     # -- gym-like surface ---------------------------------------------------------------------
     @property
@@ -53,7 +75,10 @@ class KilobotsVecEnv:
         """Device tensors in, device tensors out, no synchronisation (training-loop path)."""
         k, o, l, r, d, s = self.batch.step_device(action, self.action_mode if action is not None else None)
         self._sim_steps += self.scenario.scenes[0].steps_per_action
-        return {"kilobots": k, "objects": o, "light": l}, r, d, {"status": s}
+        obs = {"kilobots": k, "objects": o, "light": l}
+        if self.obs_flat is not None:
+            obs["flat"] = self.obs_flat
+        return obs, r, d, {"status": s}
 
     def _host_buffers(self):
         if self._host is None:
@@ -93,6 +118,8 @@ class KilobotsVecEnv:
         self.batch.step_host(act, mode, hb)
         self._sim_steps += self.scenario.scenes[0].steps_per_action
         obs = {"kilobots": hb["kilobots"], "objects": hb["objects"], "light": hb["light"]}
+        if self.obs_flat is not None:
+            obs["flat"] = self.obs_flat.cpu().numpy()
         return obs, hb["reward"], hb["done"].astype(bool), {"status": hb["status"]}
 
     def host_io_bytes(self):

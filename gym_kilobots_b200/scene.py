@@ -69,6 +69,32 @@ class LightSpec:
 
 
 @dataclass
+class TaskSpec:
+    """Task layer (an extension; the reference's reward hooks are abstract, kilobots_env.py:123-131).
+
+    reward = w_position * (d0 - d1) + w_orientation * (a0 - a1) - step_penalty (+ success_bonus), where d / a are
+    the distance / absolute angle between the subject (object `object`, or the swarm's mean position) and the
+    per-env target before and after the env-step; done on success or after max_episode_steps."""
+    mode: int = abi.KB_TASK_OBJECT_TO_TARGET
+    object: int = 0
+    max_episode_steps: int = 0
+    w_position: float = 1.0
+    w_orientation: float = 0.0
+    step_penalty: float = 0.0
+    success_bonus: float = 0.0
+    position_tolerance: float = 0.0
+    orientation_tolerance: float = np.inf
+
+    def to_def(self):
+        t = abi.KbTaskDef()
+        t.mode, t.object, t.max_episode_steps = int(self.mode), int(self.object), int(self.max_episode_steps)
+        t.w_position, t.w_orientation = float(self.w_position), float(self.w_orientation)
+        t.step_penalty, t.success_bonus = float(self.step_penalty), float(self.success_bonus)
+        t.position_tolerance, t.orientation_tolerance = float(self.position_tolerance), float(self.orientation_tolerance)
+        return t
+
+
+@dataclass
 class SceneSpec:
     bodies: List[BodySpec] = field(default_factory=list)   # objects first, then kilobots
     num_objects: int = 0

@@ -228,6 +228,47 @@ int kb_get_launch_config(const KbHandle* h, KbLaunchConfig* cfg);
 /* derived mass data per scene: f32[num_scenes,B,4] = invMass invI localCenter.x localCenter.y */
 int kb_get_mass_data(KbHandle* h, float* out);
 
+/* ---------------------------------------------------------------------------------------------
+ * Task layer -- an EXTENSION beyond the reference.
+ * The reference's get_reward / has_finished / get_info (kilobots_env.py:123-131) are abstract hooks whose
+ * in-tree implementations return constants (KB_TASK_CONST below, the default: reward = reward_const,
+ * done = 0).  The other modes evaluate a task reward, the termination flag and episode statistics inside
+ * kb_step's gather, and can emit the flat observation that YamlKilobotsEnv.observation_space describes
+ * (yaml_kilobots_env.py:163-178: kilobots (x, y) * N, light state, objects (x, y, sin theta, cos theta) * M),
+ * so that a training loop never leaves the device.  All task arithmetic is float64.
+ *   error before / after the env-step:  d = |subject - target| (m), a = |wrap(theta - target_theta)| (rad)
+ *   subject = pose of object `object` (KB_TASK_OBJECT_TO_TARGET) or the mean kilobot position
+ *             (KB_TASK_SWARM_TO_TARGET, a = 0)
+ *   reward  = w_position * (d0 - d1) + w_orientation * (a0 - a1) - step_penalty + (success ? success_bonus : 0)
+ *   success = d1 <= position_tolerance && a1 <= orientation_tolerance
+ *   done    = success || (max_episode_steps > 0 && episode length >= max_episode_steps)
+ * kb_reset zeroes the episode return / length of the envs it resets. */
+#define KB_TASK_CONST 0
+#define KB_TASK_OBJECT_TO_TARGET 1
+#define KB_TASK_SWARM_TO_TARGET 2
+typedef struct KbTaskDef {
+  int32_t mode;               /* KB_TASK_* */
+  int32_t object;             /* object index (KB_TASK_OBJECT_TO_TARGET) */
+  int32_t max_episode_steps;  /* time limit in env-steps, 0 = none */
+  int32_t reserved;
+  double w_position, w_orientation, step_penalty, success_bonus;
+  double position_tolerance, orientation_tolerance;
+} KbTaskDef;
+/* per-env episode statistics, f64[E,KB_EPISODE_STATS] */
+#define KB_EPISODE_STATS 6
+#define KB_EP_RETURN 0        /* sum of rewards since the last reset */
+#define KB_EP_LENGTH 1        /* env-steps since the last reset */
+#define KB_EP_POSITION_ERROR 2
+#define KB_EP_ORIENTATION_ERROR 3
+#define KB_EP_SUCCESS 4       /* 1 if the last step met both tolerances */
+#define KB_EP_DONE_COUNT 5    /* number of env-steps that returned done since kb_set_task */
+/* target: host f64[E,3] = (x m, y m, theta rad) per env; NULL keeps the current targets (zeros initially) */
+int kb_set_task(KbHandle* h, const KbTaskDef* task, const double* target);
+int kb_get_episode_stats(KbHandle* h, double* out /* host f64[E,KB_EPISODE_STATS] */);
+/* device f32[E, 2N + L + 4M] written by every following kb_step (NULL unbinds); see kb_flat_observation_dim */
+int kb_bind_flat_observation(KbHandle* h, float* obs_flat);
+int kb_flat_observation_dim(const KbHandle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -156,6 +156,27 @@ class OracleBatch:
         self.fn["get_mass_data"](self.h, _ptr(out))
         return out
 
+    # ---- task layer (same extension as the product library, include/kb_b200.h "Task layer")
+    def set_task(self, task, targets=None):
+        t = task.to_def()
+        tg = None if targets is None else np.ascontiguousarray(targets, dtype=np.float64).reshape(self.E, 3)
+        rc = self.fn["set_task"](self.h, C.byref(t), _ptr(tg))
+        assert rc == 0, "kbo_set_task rejected the task"
+
+    def episode_stats(self):
+        out = np.zeros((self.E, abi.KB_EPISODE_STATS), np.float64)
+        self.fn["get_episode_stats"](self.h, _ptr(out))
+        return out
+
+    def bind_flat_observation(self, enable=True):
+        if not enable:
+            self.obs_flat = None
+            self.fn["bind_flat_observation"](self.h, None)
+            return None
+        self.obs_flat = np.zeros((self.E, self.fn["flat_observation_dim"](self.h)), np.float32)
+        self.fn["bind_flat_observation"](self.h, _ptr(self.obs_flat))
+        return self.obs_flat
+
 
 def sincosf(a, libm=False):
     lib, _ = load()

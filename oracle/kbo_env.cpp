@@ -50,6 +50,9 @@ struct Env {
   std::vector<KilobotCtrl> ctrl;
   std::vector<LightState> lights;
   int status = 0;
+  // task layer (extension, include/kb_b200.h "Task layer")
+  double target[3] = {0.0, 0.0, 0.0};
+  double stats[KB_EPISODE_STATS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 };
 
 struct Handle {
@@ -58,6 +61,8 @@ struct Handle {
   int numBodies = 0, numObjects = 0, numKilobots = 0, numLights = 0;
   int lightStateDim = 0, actionDim = 0, maxContacts = 0, numProxies = 0;
   int threads = 1;
+  KbTaskDef task = {};
+  float* obsFlat = nullptr;
   // Kilobot.step single-motor constants (lib/kilobot.py:103-121), float32 b2Vec2 of translation*25
   float transRight[2], transLeft[2];
   float omegaRight, omegaLeft;
@@ -399,6 +404,29 @@ static void StepEnv(Handle* h, Env* e, const double* action, int actionMode) {
   if (w->contactCount > h->maxContacts) e->status |= KB_STATUS_CONTACT_OVERFLOW;
 }
 
+// task layer: distance (m) / |angle| (rad) of the task's subject to the env's target (include/kb_b200.h)
+static void TaskError(const Handle* h, const Env* e, double* dist, double* ang) {
+  const KbTaskDef& tk = h->task;
+  double px, py, th = 0.0;
+  if (tk.mode == KB_TASK_OBJECT_TO_TARGET) {
+    const Body* b = e->bodies[tk.object];
+    px = (double)b->xf.p.x / 25.0;
+    py = (double)b->xf.p.y / 25.0;
+    th = (double)b->sweep.a;
+  } else {
+    double sx = 0.0, sy = 0.0;
+    for (int b = h->numObjects; b < h->numBodies; ++b) {
+      sx += (double)e->bodies[b]->xf.p.x / 25.0;
+      sy += (double)e->bodies[b]->xf.p.y / 25.0;
+    }
+    px = sx / (double)h->numKilobots;
+    py = sy / (double)h->numKilobots;
+  }
+  const double dx = px - e->target[0], dy = py - e->target[1];
+  *dist = std::sqrt(dx * dx + dy * dy);
+  *ang = tk.mode == KB_TASK_OBJECT_TO_TARGET ? std::fabs(std::remainder(th - e->target[2], 6.283185307179586)) : 0.0;
+}
+
 template <class F>
 static void ParallelFor(Handle* h, F f) {
   const int E = (int)h->envs.size();
@@ -504,6 +532,7 @@ int kbo_reset(KbHandle* hh, const uint8_t* mask, const double* body_pose, const 
   const int B = h->numBodies, L = h->lightStateDim, N = h->numKilobots;
   ParallelFor(h, [&](int i) {
     if (mask && !mask[i]) return;
+    h->envs[i].stats[KB_EP_RETURN] = h->envs[i].stats[KB_EP_LENGTH] = h->envs[i].stats[KB_EP_SUCCESS] = 0.0;
     ResetEnv(h, &h->envs[i], body_pose + (size_t)i * B * 3, light_state ? light_state + (size_t)i * L : nullptr,
              kb_velocity ? kb_velocity + (size_t)i * N * 2 : nullptr);
   });
@@ -519,19 +548,33 @@ int kbo_step(KbHandle* hh, const double* action, int32_t action_mode, float* obs
   ParallelFor(h, [&](int i) {
     Env* e = &h->envs[i];
     if (!e->world) return;
+    double d0 = 0.0, a0 = 0.0;
+    if (h->task.mode != KB_TASK_CONST) TaskError(h, e, &d0, &a0);
     StepEnv(h, e, action ? action + (size_t)i * A : nullptr, action ? action_mode : KB_ACTION_NONE);
+    float* flat = h->obsFlat ? h->obsFlat + (size_t)i * (2 * N + L + 4 * M) : nullptr;
     // get_state, kilobots_env.py:115-118; Body.get_pose lib/body.py:63-65
     for (int b = 0; b < M + N; ++b) {
       const Body* body = e->bodies[b];
       float* o = b < M ? (obs_objects ? obs_objects + ((size_t)i * M + b) * 3 : nullptr)
                        : (obs_kilobots ? obs_kilobots + ((size_t)i * N + (b - M)) * 3 : nullptr);
+      const float ox = (float)((double)body->xf.p.x / 25.0), oy = (float)((double)body->xf.p.y / 25.0);
+      if (flat) {  // YamlKilobotsEnv.observation_space layout (yaml_kilobots_env.py:163-178)
+        if (b < M) {
+          float* f = flat + 2 * N + L + 4 * b;
+          f[0] = ox; f[1] = oy; f[2] = body->xf.q.s; f[3] = body->xf.q.c;
+        } else {
+          flat[2 * (b - M)] = ox;
+          flat[2 * (b - M) + 1] = oy;
+        }
+      }
       if (!o) continue;
-      o[0] = (float)((double)body->xf.p.x / 25.0);
-      o[1] = (float)((double)body->xf.p.y / 25.0);
+      o[0] = ox;
+      o[1] = oy;
       o[2] = body->sweep.a;
     }
-    if (obs_light) {
-      double* o = obs_light + (size_t)i * L;
+    double lightBuf[16];
+    if (obs_light || flat) {
+      double* o = obs_light ? obs_light + (size_t)i * L : lightBuf;
       int off = 0;
       for (int l = 0; l < h->numLights; ++l) {
         const KbLightDef& ld = h->scenes[e->scene].lights[l];
@@ -548,9 +591,32 @@ int kbo_step(KbHandle* hh, const double* action, int32_t action_mode, float* obs
         }
         off += LightStateDim(ld);
       }
+      if (flat)
+        for (int k = 0; k < L; ++k) flat[2 * N + k] = (float)o[k];
     }
-    if (reward) reward[i] = h->scenes[e->scene].desc.reward_const;
-    if (done) done[i] = 0;
+    float rew = h->scenes[e->scene].desc.reward_const;
+    uint8_t dn = 0;
+    if (h->task.mode != KB_TASK_CONST) {
+      const KbTaskDef& tk = h->task;
+      double d1, a1;
+      TaskError(h, e, &d1, &a1);
+      const bool success = d1 <= tk.position_tolerance && a1 <= tk.orientation_tolerance;
+      double r = tk.w_position * (d0 - d1);
+      r = r + tk.w_orientation * (a0 - a1);
+      r = r - tk.step_penalty;
+      if (success) r = r + tk.success_bonus;
+      const double len = e->stats[KB_EP_LENGTH] + 1.0;
+      dn = (success || (tk.max_episode_steps > 0 && len >= (double)tk.max_episode_steps)) ? 1 : 0;
+      e->stats[KB_EP_RETURN] += r;
+      e->stats[KB_EP_LENGTH] = len;
+      e->stats[KB_EP_POSITION_ERROR] = d1;
+      e->stats[KB_EP_ORIENTATION_ERROR] = a1;
+      e->stats[KB_EP_SUCCESS] = success ? 1.0 : 0.0;
+      if (dn) e->stats[KB_EP_DONE_COUNT] += 1.0;
+      rew = (float)r;
+    }
+    if (reward) reward[i] = rew;
+    if (done) done[i] = dn;
     if (status) status[i] = e->status;
   });
   return KB_OK;
@@ -721,6 +787,38 @@ int kbo_get_controllers(KbHandle* hh, double* ctrl, double* light) {
     }
   }
   return KB_OK;
+}
+
+int kbo_set_task(KbHandle* hh, const KbTaskDef* task, const double* target) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !task) return KB_ERR_INVALID;
+  if (task->mode < KB_TASK_CONST || task->mode > KB_TASK_SWARM_TO_TARGET) return KB_ERR_INVALID;
+  if (task->mode == KB_TASK_OBJECT_TO_TARGET && (task->object < 0 || task->object >= h->numObjects)) return KB_ERR_INVALID;
+  h->task = *task;
+  for (size_t i = 0; i < h->envs.size(); ++i) {
+    Env& e = h->envs[i];
+    if (target)
+      for (int k = 0; k < 3; ++k) e.target[k] = target[i * 3 + k];
+    for (int k = 0; k < KB_EPISODE_STATS; ++k) e.stats[k] = 0.0;
+  }
+  return KB_OK;
+}
+
+int kbo_get_episode_stats(KbHandle* hh, double* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  for (size_t i = 0; i < h->envs.size(); ++i)
+    for (int k = 0; k < KB_EPISODE_STATS; ++k) out[i * KB_EPISODE_STATS + k] = h->envs[i].stats[k];
+  return KB_OK;
+}
+
+int kbo_bind_flat_observation(KbHandle* hh, float* obs_flat) {
+  reinterpret_cast<Handle*>(hh)->obsFlat = obs_flat;
+  return KB_OK;
+}
+
+int kbo_flat_observation_dim(const KbHandle* hh) {
+  const Handle* h = reinterpret_cast<const Handle*>(hh);
+  return 2 * h->numKilobots + h->lightStateDim + 4 * h->numObjects;
 }
 
 int kbo_get_mass_data(KbHandle* hh, float* out) {
