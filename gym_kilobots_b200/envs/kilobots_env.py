@@ -222,12 +222,24 @@ class KilobotsEnv(_Base):
         b.set_poses(poses[None])
         self.world._mirror = b.bodies()[0]
 
-    def reset(self):
-        self.__reset_counter += 1
+    def _record_scene(self):
+        """destroy + _configure_environment (kilobots_env.py:152-155), recorded instead of simulated:
+        -> (SceneSpec, poses [B,3] m/rad, light state [L] or None, kilobot (v, omega) [N,2] or None)."""
         self.destroy()
         self._configure_environment()
-        self.__sim_steps = 0
         spec = self._scene_spec()
+        ordered = list(self._objects) + list(self._kilobots)
+        pose = np.stack([body._init_pose for body in ordered])
+        light = self._light._state_vector() if self._light else None
+        vel = None
+        if any(isinstance(k, SimpleVelocityControlKilobot) for k in self._kilobots):
+            vel = np.stack([np.asarray(getattr(k, '_velocity', np.zeros(2)), float) for k in self._kilobots])
+        return spec, pose, light, vel
+
+    def reset(self):
+        self.__reset_counter += 1
+        spec, pose, light, vel = self._record_scene()
+        self.__sim_steps = 0
         key = self._spec_key(spec)
         if self._batch is None or key != self._batch_key:
             if self._batch is not None:
@@ -237,11 +249,9 @@ class KilobotsEnv(_Base):
         self._scene_spec_cache = spec
         ordered = list(self._objects) + list(self._kilobots)
         self.world._slot = {id(body): i for i, body in enumerate(ordered)}
-        pose = np.stack([body._init_pose for body in ordered])[None]
-        light = self._light._state_vector()[None] if self._light else None
-        vel = None
-        if any(isinstance(k, SimpleVelocityControlKilobot) for k in self._kilobots):
-            vel = np.stack([np.asarray(getattr(k, '_velocity', np.zeros(2)), float) for k in self._kilobots])[None]
+        pose = pose[None]
+        light = None if light is None else light[None]
+        vel = None if vel is None else vel[None]
         # bodies at their poses, then one "step to resolve" (kilobots_env.py:157)
         self._batch.reset(pose, light, vel)
         self._sync_mirror()

@@ -37,6 +37,34 @@ class KilobotsVecEnv:
         if task is not None:
             self.set_task(task, targets)
 
+    @classmethod
+    def from_envs(cls, envs, device=0, **kwargs):
+        """Vectorise reference-style envs (instances of KilobotsEnv subclasses, e.g. E YamlKilobotsEnv built from
+        one configuration): their scenes are recorded by `scenarios.from_envs` and stepped as ONE batch.
+        DirectControlKilobotsEnv instances select per-kilobot actions."""
+        from .. import scenarios
+        from .direct_control_kilobots_env import DirectControlKilobotsEnv
+        envs = list(envs)
+        sc = scenarios.from_envs(envs)
+        mode = abi.KB_ACTION_KILOBOTS if isinstance(envs[0], DirectControlKilobotsEnv) else abi.KB_ACTION_LIGHT
+        vec = cls(sc, device=device, action_mode=mode, **kwargs)
+        vec.envs = envs
+        return vec
+
+    def resample(self, mask=None):
+        """Re-run `_configure_environment` of the (masked) source envs -> fresh initial poses / light states, the
+        way a reference `reset()` re-samples its scene.  Only for batches built by `from_envs`; scene templates
+        must not change.  Returns (body_pose [E,B,3], light_state [E,L]) for `reset` / `reset_done`."""
+        sc = self.scenario
+        for i, env in enumerate(self.envs):
+            if mask is not None and not mask[i]:
+                continue
+            _, pose, light, _ = env._record_scene()
+            sc.body_pose[i] = pose
+            if light is not None:
+                sc.light_state[i] = light
+        return sc.body_pose, sc.light_state
+
     # -- task layer (extension) -----------------------------------------------------------------
     def set_task(self, task, targets=None):
         self.batch.set_task(task, targets)
@@ -67,6 +95,8 @@ class KilobotsVecEnv:
         """KilobotsEnv.reset for every (masked) env: rebuild bodies at the poses, one settle step."""
         pose = self.scenario.body_pose if body_pose is None else body_pose
         light = self.scenario.light_state if light_state is None else light_state
+        if kb_velocity is None:
+            kb_velocity = getattr(self.scenario, "kb_velocity", None)
         self.batch.reset(pose, light, kb_velocity, mask)
         self._sim_steps = 0
         return self.get_observation()

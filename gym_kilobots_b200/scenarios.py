@@ -142,6 +142,34 @@ def c5_small(num_envs=1 << 20, seed=0, env_offset=0, **scene_kw):
     return Scenario("C5", [sc], None, pose, light, max_contacts=32)
 
 
+def from_envs(envs, name="from_envs"):
+    """Vectorise reference-style environments: every element of `envs` is a KilobotsEnv subclass instance
+    (YamlKilobotsEnv(configuration=...), QuadAssemblyKilobotsEnv(), a user's own subclass ...).  Each one's
+    `_configure_environment` is run once, exactly as `reset()` would (kilobots_env.py:150-156), including its
+    random initialisation; the recorded scenes are de-duplicated into templates and the poses stacked.
+    All envs must have the same number of objects / kilobots and the same light layout."""
+    from .envs.kilobots_env import KilobotsEnv
+    specs, keys, env_scene, poses, lights, vels = [], {}, [], [], [], []
+    for env in envs:
+        spec, pose, light, vel = env._record_scene()
+        k = KilobotsEnv._spec_key(spec)
+        if k not in keys:
+            keys[k] = len(specs)
+            specs.append(spec)
+        env_scene.append(keys[k])
+        poses.append(pose)
+        lights.append(np.zeros(0) if light is None else np.asarray(light, float))
+        vels.append(vel)
+    B, M = specs[0].num_bodies, specs[0].num_objects
+    for sp in specs:
+        if sp.num_bodies != B or sp.num_objects != M or sp.light_state_dim != specs[0].light_state_dim:
+            raise ValueError("from_envs: all environments must agree in body counts and light layout")
+    sc = Scenario(name, specs, np.asarray(env_scene, np.int32), np.stack(poses), np.stack(lights))
+    sc.kb_velocity = None if all(v is None for v in vels) else np.stack(
+        [np.zeros((B - M, 2)) if v is None else v for v in vels])
+    return sc
+
+
 def random_actions(scenario_or_dim, num_envs, steps, seed=1):
     """i.i.d. U([-0.01, 0.01]^A) per env-step: mirrors env.action_space.sample() (gym_kilobots/test.py:25)."""
     A = scenario_or_dim if isinstance(scenario_or_dim, int) else scenario_or_dim.scenes[0].action_dim

@@ -209,3 +209,44 @@ kilobots: !KilobotsConf {num: 7, mean: [0., 0.], std: .03}
     for t in range(6):
         a = np.stack([rng.uniform(0, .012, size=3), rng.uniform(-1.8, 1.8, size=3)], axis=1)
         same(eg.step(a)[0], eo.step(a)[0], "direct step %d" % t)
+
+
+def test_vec_env_from_yaml_envs(oracle, native):
+    """KilobotsVecEnv.from_envs: reference-style YamlKilobotsEnv instances (random object / light / kilobot
+    initialisation per env) vectorised into one CUDA batch == the oracle on the recorded scenario."""
+    import yaml
+    from gym_kilobots_b200.envs import KilobotsVecEnv, YamlKilobotsEnv
+    text = """
+!EvalEnv
+width: 1.0
+height: 1.0
+resolution: 600
+objects:
+  - !ObjectConf {idx: 0, color: null, shape: c_shape, width: .15, height: .15, init: random, symmetry: null}
+  - !ObjectConf {idx: 1, color: null, shape: triangle, width: .1, height: .1, init: random, symmetry: null}
+light: !LightConf {type: momentum, init: object, radius: .2}
+kilobots: !KilobotsConf {num: 12, mean: light, std: .03}
+"""
+    conf = yaml.load(text, Loader=yaml.Loader)
+    np.random.seed(4)
+    vec = KilobotsVecEnv.from_envs([YamlKilobotsEnv(configuration=conf) for _ in range(24)])
+    sc = vec.scenario
+    ob = oracle.OracleBatch(sc.scenes, sc.num_envs, sc.env_scene, sc.max_contacts, threads=8)
+    vec.reset()
+    ob.reset(sc.body_pose, sc.light_state)
+    acts = SC.random_actions(sc, sc.num_envs, 10)
+    for t in range(10):
+        obs, r, d, info = vec.step(acts[t])
+        out = ob.step(acts[t])
+        for k in ("kilobots", "objects", "light"):
+            assert np.array_equal(obs[k], out[k]), "step %d: %s" % (t, k)
+    assert np.array_equal(vec.batch.bodies(), ob.bodies())
+    # re-sample the scenes of a few envs the way a reference reset() would, and reset only those
+    mask = np.zeros(sc.num_envs, np.uint8)
+    mask[::5] = 1
+    pose, light = vec.resample(mask)
+    vec.reset_done(mask, pose, light)
+    ob.reset(pose, light, mask=mask)
+    obs, _, _, _ = vec.step(acts[0])
+    out = ob.step(acts[0])
+    assert np.array_equal(obs["kilobots"], out["kilobots"]) and np.array_equal(vec.batch.bodies(), ob.bodies())

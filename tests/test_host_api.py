@@ -160,3 +160,46 @@ def test_scenarios_are_partition_invariant():
     full3 = SC.c3_shapes(9, seed=1, num_kilobots=8)
     part3 = SC.c3_shapes(3, seed=1, env_offset=6, num_kilobots=8)
     assert np.array_equal(full3.body_pose[6:], part3.body_pose) and np.array_equal(full3.env_scene[6:], part3.env_scene)
+
+
+_YAML_VEC = """
+!EvalEnv
+width: 1.0
+height: 1.0
+resolution: 600
+objects:
+  - !ObjectConf {idx: 0, color: null, shape: t_shape, width: .15, height: .15, init: random, symmetry: null}
+  - !ObjectConf {idx: 1, color: null, shape: square, width: .1, height: .1, init: random, symmetry: null}
+light: !LightConf {type: circular, init: object, radius: .2}
+kilobots: !KilobotsConf {num: 9, mean: light, std: .03}
+"""
+
+
+def test_from_envs_vectorises_yaml_envs(oracle):
+    """scenarios.from_envs / KilobotsVecEnv.from_envs: E YamlKilobotsEnv built from one
+    configuration, each with its own random initialisation (yaml_kilobots_env.py:194-198,256-265,327-354),
+    become ONE batch whose env e behaves exactly like stepping reference-style env e on its own."""
+    from gym_kilobots_b200 import scenarios as SC
+    from gym_kilobots_b200.envs import YamlKilobotsEnv
+    conf = yaml.load(_YAML_VEC, Loader=yaml.Loader)
+    E = 5
+    cls = _with_oracle(YamlKilobotsEnv, oracle)
+    np.random.seed(11)
+    sc = SC.from_envs([cls(configuration=conf) for _ in range(E)])
+    assert sc.body_pose.shape == (E, 11, 3) and sc.light_state.shape == (E, 2)
+    assert len(sc.scenes) == 1 and np.array_equal(sc.env_scene, np.zeros(E, np.int32))
+    assert len(np.unique(sc.body_pose[:, 0, 0])) == E          # every env drew its own object pose
+    ob = oracle.OracleBatch(sc.scenes, E, sc.env_scene, sc.max_contacts)
+    ob.reset(sc.body_pose, sc.light_state)
+    acts = SC.random_actions(sc, E, 3)
+    np.random.seed(11)
+    singles = [cls(configuration=conf) for _ in range(E)]
+    for env in singles:
+        env.reset()
+    for t in range(3):
+        out = ob.step(acts[t])
+        for e, env in enumerate(singles):
+            o, r, d, info = env.step(acts[t, e])
+            assert np.allclose(o["kilobots"], out["kilobots"][e], atol=1e-7)   # float32 observation vs float64 pose
+            assert np.allclose(o["objects"], out["objects"][e], atol=1e-7)
+            assert np.array_equal(o["light"], out["light"][e])
