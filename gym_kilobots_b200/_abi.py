@@ -145,6 +145,7 @@ PROTOTYPES = {
     "get_episode_stats": (C.c_int, [_VP, _VP]),
     "bind_flat_observation": (C.c_int, [_VP, _VP]),
     "flat_observation_dim": (C.c_int, [_VP]),
+    "render": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP]),
 }
 # exported by the product library only (the oracle has no state blob)
 class KbLaunchConfig(C.Structure):

@@ -224,6 +224,15 @@ class NativeBatch:
         _check(_fn["bind_flat_observation"](self.h, C.c_void_p(self.obs_flat.data_ptr())), "kb_bind_flat_observation")
         return self.obs_flat
 
+    def render(self, env_ids=(0,), width=1200, height=900):
+        """uint8 CUDA tensor [len(env_ids), height, width, 3]: the picture KilobotsEnv.render would draw
+        (kilobots_env.py:221-275; default size = screen_size :22), rasterised on the device."""
+        ids = np.ascontiguousarray(env_ids, dtype=np.int32).reshape(-1)
+        out = self.torch.empty((len(ids), height, width, 3), dtype=self.torch.uint8, device=self.device)
+        _check(_fn["render"](self.h, _hptr(ids), len(ids), width, height, C.c_void_p(out.data_ptr()), self._stream()),
+               "kb_render")
+        return out
+
     def host_layout(self):
         """(offsets of kilobots, objects, light, reward, status, done; total bytes) of the packed host block."""
         off = (C.c_int64 * 6)()

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kb_toi.cuh"
+#include "kb_render.cuh"
 
 namespace kb {
 
@@ -247,6 +248,9 @@ struct Handle {
   double* dObsL = nullptr;
   uint8_t* dDone = nullptr;
   int32_t* dStatus = nullptr;
+  float wall[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // table rectangle x0 y0 x1 y1, b2 units (render window)
+  int32_t* dRenderIds = nullptr;
+  int renderIdsCap = 0;
   // task layer (extension)
   TaskConst task = {};
   double* dTask = nullptr;   // [E][KB_TASK_WORDS]
@@ -782,6 +786,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     h->dStatus = reinterpret_cast<int32_t*>(h->dOut + h->hostOff[4]);
     h->dDone = h->dOut + h->hostOff[5];
   }
+  h->wall[0] = s0.wall_x0; h->wall[1] = s0.wall_y0; h->wall[2] = s0.wall_x1; h->wall[3] = s0.wall_y1;
   CUDA_TRY(cudaMalloc(&h->dTask, sizeof(double) * KB_TASK_WORDS * (size_t)num_envs));
   CUDA_TRY(cudaMemset(h->dTask, 0, sizeof(double) * KB_TASK_WORDS * (size_t)num_envs));
 #ifdef KB_PROFILE
@@ -809,7 +814,7 @@ int kb_destroy(KbHandle* hh) {
   if (!h) return KB_OK;
   cudaSetDevice(h->device);
   cudaFree(h->dBlobs); cudaFree(h->dEnvScene); cudaFree(h->dProxies); cudaFree(h->dBodies);
-  cudaFree(h->dScenes); cudaFree(h->dLights); cudaFree(h->dAction); cudaFree(h->dOut); cudaFree(h->dTask);
+  cudaFree(h->dScenes); cudaFree(h->dLights); cudaFree(h->dAction); cudaFree(h->dOut); cudaFree(h->dTask); cudaFree(h->dRenderIds);
   delete h;
   return KB_OK;
 }
@@ -1173,6 +1178,45 @@ int kb_flat_observation_dim(const KbHandle* hh) {
   const Handle* h = reinterpret_cast<const Handle*>(hh);
   if (!h) return fail(KB_ERR_INVALID, "kb_flat_observation_dim: null handle");
   return 2 * h->L.N + h->L.L + 4 * h->L.M;
+}
+
+// ---- off-screen rasteriser (kb_render.cuh) ---------------------------------------------------------------
+int kb_render(KbHandle* hh, const int32_t* env_ids, int32_t num_images, int32_t width, int32_t height, uint8_t* rgb,
+              void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !env_ids || !rgb || num_images < 1 || width < 1 || height < 1)
+    return fail(KB_ERR_INVALID, "kb_render: invalid arguments");
+  if (num_images > 65535) return fail(KB_ERR_INVALID, "kb_render: at most 65535 images per call");
+  for (int i = 0; i < num_images; ++i)
+    if (env_ids[i] < 0 || env_ids[i] >= h->numEnvs) return fail(KB_ERR_INVALID, "kb_render: env id out of range");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (num_images > h->renderIdsCap) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(h->dRenderIds);
+    h->dRenderIds = nullptr;
+    CUDA_TRY(cudaMalloc(&h->dRenderIds, sizeof(int32_t) * (size_t)num_images));
+    h->renderIdsCap = num_images;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->dRenderIds, env_ids, sizeof(int32_t) * (size_t)num_images, cudaMemcpyHostToDevice, st));
+  RenderArgs a;
+  a.L = h->L;
+  a.blobs = h->dBlobs;
+  a.envScene = h->dEnvScene;
+  a.proxies = h->dProxies;
+  a.bodies = h->dBodies;
+  a.scenes = h->dScenes;
+  a.lights = h->dLights;
+  a.envIds = h->dRenderIds;
+  a.numImages = num_images;
+  a.width = width;
+  a.height = height;
+  a.x0 = h->wall[0]; a.y0 = h->wall[1]; a.x1 = h->wall[2]; a.y1 = h->wall[3];
+  a.out = rgb;
+  const dim3 block(16, 16), grid((width + 15) / 16, (height + 15) / 16, num_images);
+  kb_render_kernel<<<grid, block, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return KB_OK;
 }
 
 int kb_get_mass_data(KbHandle* hh, float* out) {

@@ -291,7 +291,17 @@ class KilobotsEnv(_Base):
         return observation, reward, done, info
 
     def render(self, mode=None):
-        raise NotImplementedError("rendering (kb_rendering.KilobotsViewer) is outside the accelerated hot path")
+        """mode='rgb_array': the frame the reference draws through kb_rendering.KilobotsViewer (:221-275), rasterised
+        on the device (kb_render) and returned as uint8 [screen_height, screen_width, 3].  There is no window:
+        'human' mode (pygame display, real-time pacing, mp4 recording) is outside the accelerated path."""
+        if mode is None:
+            mode = self.render_mode
+        if mode != 'rgb_array':
+            raise NotImplementedError("only render(mode='rgb_array') is provided; the pygame viewer is out of scope")
+        if self._batch is None:
+            raise RuntimeError("KilobotsEnv.render called before reset()")
+        img = self._batch.render((0,), self.screen_width, self.screen_height)
+        return np.asarray(img.cpu() if hasattr(img, "cpu") else img)[0]
 
     def get_objects(self) -> [Body]:
         return self._objects

@@ -159,6 +159,12 @@ class KilobotsVecEnv:
         d2h = sum(hb[k].nbytes for k in ("kilobots", "objects", "light", "reward", "done", "status"))
         return h2d, d2h
 
+    def render(self, env_ids=(0,), width=1200, height=900, mode="rgb_array"):
+        """The frame(s) KilobotsEnv.render would draw (kilobots_env.py:221-275) for the given envs, rasterised on
+        the GPU: uint8 [len(env_ids), height, width, 3] (numpy for 'rgb_array', CUDA tensor for 'tensor')."""
+        img = self.batch.render(env_ids, width, height)
+        return img if mode == "tensor" else img.cpu().numpy()
+
     def get_state(self):
         b = self.batch.bodies()
         _, light = self.batch.controllers()

@@ -269,6 +269,13 @@ int kb_get_episode_stats(KbHandle* h, double* out /* host f64[E,KB_EPISODE_STATS
 int kb_bind_flat_observation(KbHandle* h, float* obs_flat);
 int kb_flat_observation_dim(const KbHandle* h);
 
+/* Off-screen rasteriser: the picture KilobotsEnv.render draws through
+ * kb_rendering.KilobotsViewer (kilobots_env.py:221-275) -- table, objects, kilobots, light -- for num_images
+ * environments, straight from the device state.  env_ids: host i32[num_images]; rgb: DEVICE u8[num_images,
+ * height, width, 3], row 0 = top of the arena (y = +world_height / 2).  Asynchronous on `stream`. */
+int kb_render(KbHandle* h, const int32_t* env_ids, int32_t num_images, int32_t width, int32_t height,
+              uint8_t* rgb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,6 +168,12 @@ class OracleBatch:
         self.fn["get_episode_stats"](self.h, _ptr(out))
         return out
 
+    def render(self, env_ids=(0,), width=1200, height=900):
+        ids = np.ascontiguousarray(env_ids, dtype=np.int32).reshape(-1)
+        out = np.zeros((len(ids), height, width, 3), np.uint8)
+        self.fn["render"](self.h, _ptr(ids), len(ids), width, height, _ptr(out), None)
+        return out
+
     def bind_flat_observation(self, enable=True):
         if not enable:
             self.obs_flat = None

@@ -821,6 +821,78 @@ int kbo_flat_observation_dim(const KbHandle* hh) {
   return 2 * h->numKilobots + h->lightStateDim + 4 * h->numObjects;
 }
 
+// Off-screen rasteriser mirror (include/kb_b200.h kb_render): same float32 expressions, pixel by pixel, from the
+// oracle's own objects.  Draw semantics: kilobots_env.py:221-275, lib/body.py:156-157,202-203,279-281,
+// lib/kilobot.py:129-145,205-210, lib/light.py:95-96,194-195.  rgb is a HOST buffer here.
+int kbo_render(KbHandle* hh, const int32_t* env_ids, int32_t num_images, int32_t width, int32_t height, uint8_t* rgb,
+               void* stream) {
+  (void)stream;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  const float S = 25.0f;
+  for (int img = 0; img < num_images; ++img) {
+    const Env* e = &h->envs[env_ids[img]];
+    const Scene& sc = h->scenes[e->scene];
+    const float x0 = sc.desc.wall_x0, y0 = sc.desc.wall_y0, x1 = sc.desc.wall_x1, y1 = sc.desc.wall_y1;
+    for (int py = 0; py < height; ++py)
+      for (int px = 0; px < width; ++px) {
+        const float x = x0 + ((float)px + 0.5f) * ((x1 - x0) / (float)width);
+        const float y = y1 - ((float)py + 0.5f) * ((y1 - y0) / (float)height);
+        float c[3] = {255.0f, 255.0f, 255.0f};
+        const float hbx = std::fmax(0.0015f * S, (x1 - x0) / (float)width);
+        const float hby = std::fmax(0.0015f * S, (y1 - y0) / (float)height);
+        if (x - x0 < hbx || x1 - x < hbx || y - y0 < hby || y1 - y < hby) c[0] = c[1] = c[2] = 0.0f;
+        for (int b = 0; b < h->numObjects; ++b) {
+          const Body* body = e->bodies[b];
+          const float dx = x - body->xf.p.x, dy = y - body->xf.p.y;
+          for (const Fixture* f : body->fixtures) {
+            bool inside;
+            if (f->shape.type == kCircle) {
+              inside = dx * dx + dy * dy <= f->shape.radius * f->shape.radius;
+            } else {
+              const float lx = body->xf.q.c * dx + body->xf.q.s * dy, ly = -body->xf.q.s * dx + body->xf.q.c * dy;
+              inside = true;
+              for (int i = 0; i < f->shape.count; ++i)
+                inside = inside && (f->shape.normals[i].x * (lx - f->shape.vertices[i].x) +
+                                    f->shape.normals[i].y * (ly - f->shape.vertices[i].y) <= 0.0f);
+            }
+            if (inside) { c[0] = 93.0f; c[1] = 133.0f; c[2] = 195.0f; }
+          }
+        }
+        for (int b = h->numObjects; b < h->numBodies; ++b) {
+          const Body* body = e->bodies[b];
+          const float dx = x - body->xf.p.x, dy = y - body->xf.p.y;
+          const float d2 = dx * dx + dy * dy;
+          const float R = (0.0165f + 0.002f) * S, Rin = (0.0165f + 0.002f - 0.005f) * S;
+          if (d2 > R * R) continue;
+          c[0] = c[1] = c[2] = 150.0f;
+          if (d2 >= Rin * Rin) c[0] = c[1] = c[2] = 100.0f;
+          if (sc.bodies[b].kind != KB_KILOBOT_SIMPLE_PHOTOTAXIS) {
+            const float lx = body->xf.q.c * dx + body->xf.q.s * dy, ly = -body->xf.q.s * dx + body->xf.q.c * dy;
+            const float front = (0.0165f - 0.005f) * S, hw = 0.0025f * S;
+            if (lx >= 0.0f && lx <= front && ly >= -hw && ly <= hw) c[0] = c[1] = c[2] = 255.0f;
+          }
+        }
+        for (int l = 0; l < h->numLights; ++l) {
+          const KbLightDef& ld = sc.lights[l];
+          if (ld.type == KB_LIGHT_LINEAR) continue;
+          const LightState& ls = e->lights[l];
+          const float lx = (float)(ls.pos[0] * 25.0), ly = (float)(ls.pos[1] * 25.0);
+          const float R = (float)(ld.radius * 25.0);
+          const float dx = x - lx, dy = y - ly;
+          if (dx * dx + dy * dy <= R * R) {
+            const float al = 150.0f / 255.0f, be = 1.0f - 150.0f / 255.0f;
+            c[0] = 255.0f * al + c[0] * be;
+            c[1] = 255.0f * al + c[1] * be;
+            c[2] = 30.0f * al + c[2] * be;
+          }
+        }
+        uint8_t* o = rgb + (((size_t)img * height + py) * width + px) * 3;
+        for (int k = 0; k < 3; ++k) o[k] = (uint8_t)(int)(c[k] + 0.5f);
+      }
+  }
+  return KB_OK;
+}
+
 int kbo_get_mass_data(KbHandle* hh, float* out) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   // derived per scene by building a throw-away world at the origin
