@@ -23,9 +23,11 @@
 namespace kb {
 
 // ----------------------------------------------------------------------------------- kernels
-// threads per block: two warps (one for 4-lane groups, whose 8 envs per warp already fill a block's shared memory)
+// threads per block: two warps for every lane-group width.  The warps of a block rendezvous at the phase boundaries
+// (KB_T in kb_step.cuh) and so share instruction-cache lines: with one warp per block the 4-lane kernel spent
+// 10 of 17 cycles per issue waiting for instructions (profiles/ncu_c5_r01_block32.txt; +25 % throughput at 64).
 #ifndef KB_BLOCK4
-#define KB_BLOCK4 32
+#define KB_BLOCK4 64
 #endif
 #ifndef KB_BLOCK8
 #define KB_BLOCK8 64
@@ -39,13 +41,16 @@ namespace kb {
 #ifndef KB_MINBLOCKS8
 #define KB_MINBLOCKS8 3
 #endif
-#define KB_BLOCK_OF(LPE) ((LPE) == 4 ? KB_BLOCK4 : ((LPE) == 8 ? KB_BLOCK8 : ((LPE) == 16 ? KB_BLOCK16 : 64)))
+#ifndef KB_BLOCK32
+#define KB_BLOCK32 64
+#endif
+#define KB_BLOCK_OF(LPE) ((LPE) == 4 ? KB_BLOCK4 : ((LPE) == 8 ? KB_BLOCK8 : ((LPE) == 16 ? KB_BLOCK16 : KB_BLOCK32)))
 
 // The batch is padded to a whole number of blocks (numEnvs <= grid * EPB): every lane of the step kernel owns
 // a real environment, so the groups of a warp can run in lock step.  Padding envs replicate the inputs of the
 // last real env and never write outputs.
 template <int LPE>
-__global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? 8 : (KB_BLOCK_OF(LPE) > 64 ? 1 : (LPE == 16 ? KB_MINBLOCKS16 : KB_MINBLOCKS8)))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? (512 / KB_BLOCK32) : (KB_BLOCK_OF(LPE) > 64 ? 1 : (LPE == 16 ? KB_MINBLOCKS16 : KB_MINBLOCKS8)))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
   constexpr int EPB = KB_BLOCK_OF(LPE) / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
