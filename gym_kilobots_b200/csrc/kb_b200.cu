@@ -41,6 +41,9 @@ namespace kb {
 #ifndef KB_MINBLOCKS8
 #define KB_MINBLOCKS8 3
 #endif
+#ifndef KB_MINBLOCKS4
+#define KB_MINBLOCKS4 6   /* 6 blocks of 64 threads per SM: <= 168 registers (C5: 96 resident envs per SM) */
+#endif
 #ifndef KB_BLOCK32
 #define KB_BLOCK32 64
 #endif
@@ -50,7 +53,7 @@ namespace kb {
 // a real environment, so the groups of a warp can run in lock step.  Padding envs replicate the inputs of the
 // last real env and never write outputs.
 template <int LPE>
-__global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? (512 / KB_BLOCK32) : (KB_BLOCK_OF(LPE) > 64 ? 1 : (LPE == 16 ? KB_MINBLOCKS16 : KB_MINBLOCKS8)))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? (512 / KB_BLOCK32) : (KB_BLOCK_OF(LPE) > 64 ? 1 : (LPE == 16 ? KB_MINBLOCKS16 : (LPE == 4 ? KB_MINBLOCKS4 : KB_MINBLOCKS8))))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
   constexpr int EPB = KB_BLOCK_OF(LPE) / LPE;
   const int slot = threadIdx.x / LPE;
   const int env = blockIdx.x * EPB + slot;
@@ -609,7 +612,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   L.Pp = P;
   L.Cmax = round4(max_contacts > 0 ? max_contacts : std::min(P * (P - 1) / 2, 8 * B + 32));
   if (L.Cmax > 65535) L.Cmax = 65532;
-  L.Kmax = round4(std::min(std::min(L.Cmax, 3 * B + 12), (int)KB_MAX_SOLVER));
+  L.Kmax = round4(std::min(std::min(L.Cmax, 3 * B + 9), (int)KB_MAX_SOLVER));
   L.KW = round4((L.Kmax + 31) / 32);  // words per body mask over the touching list, padded to whole 128-bit loads
   {
     // general constraints can only arise between proxies that are not frictionless circles-with-zero-restitution

@@ -221,6 +221,7 @@ struct Sim {
   __device__ __forceinline__ void loadState() {
     const float4* src = reinterpret_cast<const float4*>(blob);
     const int n4 = L.stateWords >> 2;
+#pragma unroll 1
     for (int i = g.lane; i < n4; i += LPE) sts_f4(sa + 16u * (uint32_t)i, src[i]);
     g.sync();
   }
@@ -228,6 +229,7 @@ struct Sim {
     g.sync();
     float4* dst = reinterpret_cast<float4*>(blob);
     const int n4 = L.stateWords >> 2;
+#pragma unroll 1
     for (int i = g.lane; i < n4; i += LPE) dst[i] = lds_f4(sa + 16u * (uint32_t)i);
     if (g.lane == 0) {
       unsigned long long* c = reinterpret_cast<unsigned long long*>(blob + L.oCnt);
@@ -244,6 +246,7 @@ struct Sim {
   // scratch that is constant for the launch: body constants, static-table slot, proxy->body map,
   // adjacency masks of the persistent contact list
   __device__ __forceinline__ void initScratch() {
+#pragma unroll 1
     for (int b = g.lane; b <= L.B; b += LPE) {
       if (b < L.B) {
         const BodyConst* c = bc + b;
@@ -262,17 +265,21 @@ struct Sim {
         sweep4(b) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
     }
+#pragma unroll 1
     for (int p = g.lane; p < L.P; p += LPE) {
       sts_u8(wa(L.sPb) + (uint32_t)p, (uint32_t)__ldg(&px[p].body));
       sts_u8(wa(L.sPt) + (uint32_t)p, (uint32_t)__ldg(&px[p].type) | (__ldg(&px[p].friction) == 0.0f ? 4u : 0u) |
                                           (__ldg(&px[p].restitution) == 0.0f ? 8u : 0u));
       sts_f32(wa(L.sPr + p), __ldg(&px[p].radius));
     }
+#pragma unroll 1
     for (int p = g.lane; p < 2 * L.P; p += LPE) word(L.sAdj + p) = 0u;
+#pragma unroll 1
     for (int w = g.lane; w < LC_WORDS * L.numLights; w += LPE)
       word(L.sLc + w) = __ldg(reinterpret_cast<const uint32_t*>(lights) + w);
     g.sync();
     const int nC = (int)hdr(H_NC);
+#pragma unroll 1
     for (int i = g.lane; i < nC; i += LPE) {
       const uint32_t w = cw(i);
       const int pa = CW_PA(w), pb = CW_PB(w);
@@ -392,6 +399,7 @@ struct Sim {
   __device__ __forceinline__ void setKilobotActions(const double* action) {
     const double hpi = 0.5 * 3.141592653589793;
     const double pi = 3.141592653589793;
+#pragma unroll 1
     for (int k = g.lane; k < L.N; k += LPE) {
       const int kind = bkind(L.M + k);
       double* c = ctrl(k);
@@ -419,6 +427,7 @@ struct Sim {
 
   __device__ __forceinline__ void senseControl() {
     const SF64Arr ls = lightState();
+#pragma unroll 1
     for (int k = g.lane; k < L.N; k += LPE) {
       const int b = L.M + k;
       const int kind = bkind(b);
@@ -613,10 +622,12 @@ struct Sim {
     if (nC == 0) return;
     // any sleeping dynamic body?
     bool sleepy = false;
+#pragma unroll 1
     for (int b = g.lane; b < L.B; b += LPE) sleepy |= !awake(b);
     const bool anyAsleep = g.any(sleepy);
     // stk(b) doubles as wakeAt[b]: per body, the highest contact index that woke it
     if (anyAsleep) {
+#pragma unroll 1
       for (int b = g.lane; b <= L.B; b += LPE) stk(b) = awake(b) ? 0x7FFFFFFF : -1;
       g.sync();
     }
@@ -626,6 +637,7 @@ struct Sim {
     const int top = ((nC - 1) / LPE) * LPE;
     for (int pass = 0;; ++pass) {
       bool woke = false;
+#pragma unroll 1
       for (int base = top; base >= 0; base -= LPE) {
         const int i = base + g.lane;
         bool doit = false;
@@ -675,6 +687,7 @@ struct Sim {
     }
     g.sync();
     if (anyAsleep) {
+#pragma unroll 1
       for (int b = g.lane; b < L.B; b += LPE)
         if ((int32_t)stk(b) >= 0) wake(b);
       g.sync();
@@ -683,6 +696,7 @@ struct Sim {
     const bool compact = g.any(anyDestroyed);
     if (!compact && !anyAsleep) return;
     int out = 0;
+#pragma unroll 1
     for (int base = 0; base < nC; base += LPE) {
       const int i = base + g.lane;
       uint32_t w = 0u;
@@ -1345,13 +1359,16 @@ struct Sim {
     const int B = L.B;
     const int KW = L.KW;
     // ---- touching list in world-list order (descending index) and per-body masks over it
+#pragma unroll 1
     for (int i = g.lane; i < (B + 1) * KW; i += LPE) word(L.sBmask + i) = 0u;
+#pragma unroll 1
     for (int b = g.lane; b <= B; b += LPE) {
       isl(b) = -1;
       lastLvl(b) = 0u;
     }
     g.sync();
     int K = 0;
+#pragma unroll 1
     for (int base = 0; base < nC; base += LPE) {
       const int i = nC - 1 - (base + g.lane);
       bool t = false;
@@ -1384,8 +1401,10 @@ struct Sim {
       if (g.lane == 0) hdr(H_STATUS) |= KB_STATUS_SOLVER_OVERFLOW;
       K = L.Kmax;
     }
+#pragma unroll 1
     for (int l = g.lane; l <= K + 1; l += LPE) lvlTab(l) = 0u;
     unsigned long long awakeMask = 0ull;  // awake dynamic bodies (every lane holds the whole mask)
+#pragma unroll 1
     for (int bb = 0; bb < B; bb += LPE) {
       const int b = bb + g.lane;
       awakeMask |= (unsigned long long)g.ballot(b < B && awake(b)) << bb;
@@ -1488,6 +1507,7 @@ struct Sim {
     nLvl += misc(3);
     // ---- b2Island::Solve: integrate velocities (damping), remember the sweep start
     const float h = L.dt;
+#pragma unroll 1
     for (int b = g.lane; b < B; b += LPE) {
       if (isl(b) < 0) continue;
       const float4 p = pos4(b);
@@ -1505,6 +1525,7 @@ struct Sim {
     // ---- constraints.  Entry e is owned by lane e % LPE for the whole solve.
     {
       uint32_t pts = 0u;
+#pragma unroll 1
       for (int e = g.lane; e < nOrd; e += LPE) {
         const uint32_t item = ent(e);
         const int ci = (int)entC(e);
@@ -1552,11 +1573,13 @@ struct Sim {
       }
     }
     KB_T(5);
+#pragma unroll 1
     for (int e = g.lane; e < nOrd; e += LPE) {
       if ((ent(e) & IT_GEN) != 0u) storeGeneralNI(*this, genSlot(e));
       else storeSimple(e, (int)entC(e));
     }
     // ---- integrate positions
+#pragma unroll 1
     for (int b = g.lane; b < B; b += LPE) {
       if (isl(b) < 0) continue;
       float4 p = pos4(b);
@@ -1611,11 +1634,13 @@ struct Sim {
         unsolved &= badAll;
       }
       // bit 1: positionSolved (sleep bookkeeping below adds bit 2: minSleepTime < timeToSleep)
+#pragma unroll 1
       for (int i = g.lane; i < nIslands; i += LPE) islflag(i) = ((unsolved >> i) & 1ull) != 0ull ? 0u : 2u;
       g.usync();
     }
     KB_T(7);
     // ---- copy back: SynchronizeTransform; sleep bookkeeping
+#pragma unroll 1
     for (int b = g.lane; b < B; b += LPE) {
       const int island = isl(b);
       if (island < 0) continue;
@@ -1640,6 +1665,7 @@ struct Sim {
     }
     g.sync();
     if (L.enableSleep) {
+#pragma unroll 1
       for (int b = g.lane; b < B; b += LPE) {
         const int island = isl(b);
         if (island < 0) continue;
@@ -1694,6 +1720,7 @@ struct Sim {
   // (toiMode: for bodies flagged in isl() by the TOI mini-island; xf1 is rebuilt from (c0, a0)).
   __device__ __forceinline__ void synchronizeFixtures(bool toiMode) {
     uint32_t mlo = 0u, mhi = 0u;
+#pragma unroll 1
     for (int p = g.lane; p < L.P; p += LPE) {
       const int b = pbody(p);
       if (b == S) continue;
@@ -1757,6 +1784,7 @@ struct Sim {
     int nC = (int)hdr(H_NC);
     bool overflow = false;
     uint32_t tests = 0u;
+#pragma unroll 1
     for (int ib = 0; ib < P - 1; ib += LPE) {
       if ((moved >> ib) == 0ull) break;  // neither a row from here on nor any of their columns moved
       const int i = ib + g.lane;
@@ -1830,6 +1858,7 @@ struct Sim {
       // any contact with the table at all?  (the common case is none: skip the out-of-line TOI path)
       const int nC = (int)hdr(H_NC);
       bool wallContact = false;
+#pragma unroll 1
       for (int i = g.lane; i < nC; i += LPE) wallContact |= pbody(CW_PA(cw(i))) == S;
       if (g.any(wallContact)) nToi += solveTOINI(*this);
       g.usync();
@@ -1878,6 +1907,7 @@ struct Sim {
     const int M = L.M, N = L.N;
     bool bad = false;
     float* flat = a.obsFlat ? a.obsFlat + (size_t)env * (2 * N + L.L + 4 * M) : nullptr;
+#pragma unroll 1
     for (int b = g.lane; b < L.B; b += LPE) {
       const float4 x = xf4(b);
       const float ang = pos4(b).get(2);
@@ -1904,6 +1934,7 @@ struct Sim {
     if (g.any(bad) && g.lane == 0) hdr(H_STATUS) |= KB_STATUS_NONFINITE;
     if (a.obsLight || flat) {
       const SF64Arr ls = lightState();
+#pragma unroll 1
       for (int i = g.lane; i < L.L; i += LPE) {
         const double v = ls[i];
         if (a.obsLight) a.obsLight[(size_t)env * L.L + i] = v;

@@ -76,6 +76,14 @@ for ln in dis[i0 + 1:]:
                         chain.append(fl)
             pend = []
         insts.append((int(m.group(1), 16), chain, m.group(2)))
+if rep == "-":   # static mode: SASS instruction count per phase, no report needed
+    cnt = defaultdict(int)
+    for addr, ch, txt in insts:
+        cnt[phase_of(ch)] += 1
+    for p_, c_ in sorted(cnt.items(), key=lambda kv: -kv[1]):
+        print("%-28s %8d" % (p_, c_))
+    print("%-28s %8d" % ("total", len(insts)))
+    sys.exit(0)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = None
