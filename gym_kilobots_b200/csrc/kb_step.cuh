@@ -79,6 +79,7 @@ struct KernelArgs {
 #define IT_BB(x) ((int)(((x) >> 6) & 63u))
 #define IT_ISL(x) ((int)(((x) >> 12) & 63u))
 #define IT_GEN (1u << 18)
+#define IT_FAST (1u << 19)   /* set by storeSimple: circle manifold between two bodies whose transforms need no rotation */
 #define IT_ROW(x) ((int)((x) >> 24))
 #define IT_NONE 0xFFFFFFFFu
 
@@ -846,7 +847,7 @@ struct Sim {
   }
 
   // b2ContactSolver::StoreImpulses, then re-purpose the records for the position solver
-  __device__ __forceinline__ void storeSimple(int e, int ci) {
+  __device__ __forceinline__ void storeSimple(int e, int ci, uint32_t item) {
     float* rec = manifoldRec(ci);
     rec[MR_P0N] = rec4(2 * e).get(3);
     const float4 r0 = reinterpret_cast<const float4*>(rec)[0];
@@ -854,6 +855,49 @@ struct Sim {
     const uint32_t w = cw(ci);
     rec4(2 * e) = r0;
     rec4(2 * e + 1) = make_float4(pradius(CW_PA(w)), pradius(CW_PB(w)), u2f(tp & 0xFFu), 0.0f);
+    // the position sweeps decide once per solve, not once per row-step, whether this entry is the
+    // kilobot-against-kilobot case of solvePositionSimple (the predicate is copied from there)
+    const int bA = IT_BA(item), bB = IT_BB(item);
+    const float4 kA = bc4(bA), kB = bc4(bB);
+    const bool trigA = bA != S && ((int)(tp & 0xFFu) != MANIFOLD_CIRCLES || r0.z != 0.0f || r0.w != 0.0f ||
+                                   kA.z != 0.0f || kA.w != 0.0f);
+    const bool trigB = bB != S && (kB.z != 0.0f || kB.w != 0.0f);
+    if ((int)(tp & 0xFFu) == MANIFOLD_CIRCLES && bA != S && !trigA && !trigB) ent(e) = item | IT_FAST;
+  }
+
+  // solvePositionSimple for an IT_FAST entry: the same operations in the same order, without the case analysis
+  __device__ __forceinline__ bool solvePositionFast(int e, uint32_t item) {
+    const int bA = IT_BA(item), bB = IT_BB(item);
+    const float4 r1 = rec4(2 * e + 1);
+    const float4 kA = bc4(bA), kB = bc4(bB);
+    float4 pA4 = pos4(bA), pB4 = pos4(bB);
+    const float mA = kA.x, iA = kA.y, mB = kB.x, iB = kB.y;
+    V2 cA = mk(pA4.x, pA4.y), cB = mk(pB4.x, pB4.y);
+    V2 normal = cB - cA;
+    normalize(normal);
+    const V2 point = 0.5f * (cA + cB);
+    const float separation = dot(cB - cA, normal) - r1.x - r1.y;
+    const bool ok = separation >= -3.0f * KB_LINEAR_SLOP;
+    const float C = b2clamp(KB_BAUMGARTE * (separation + KB_LINEAR_SLOP), -KB_MAX_LINEAR_CORRECTION, 0.0f);
+    if (C == 0.0f) return ok;
+    const V2 rA = point - cA;
+    const V2 rB = point - cB;
+    const float rnA = cross(rA, normal);
+    const float rnB = cross(rB, normal);
+    const float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+    const float impulse = K > 0.0f ? -C / K : 0.0f;
+    const V2 P = impulse * normal;
+    cA = cA - mA * P;
+    pA4.z -= iA * cross(rA, P);
+    cB = cB + mB * P;
+    pB4.z += iB * cross(rB, P);
+    pA4.x = cA.x; pA4.y = cA.y;
+    pos4(bA) = pA4;
+    if (bB != S) {
+      pB4.x = cB.x; pB4.y = cB.y;
+      pos4(bB) = pB4;
+    }
+    return ok;
   }
 
   // one constraint of b2ContactSolver::SolvePositionConstraints.  Returns false if the separation is
@@ -1576,7 +1620,7 @@ struct Sim {
 #pragma unroll 1
     for (int e = g.lane; e < nOrd; e += LPE) {
       if ((ent(e) & IT_GEN) != 0u) storeGeneralNI(*this, genSlot(e));
-      else storeSimple(e, (int)entC(e));
+      else storeSimple(e, (int)entC(e), ent(e));
     }
     // ---- integrate positions
 #pragma unroll 1
@@ -1622,8 +1666,9 @@ struct Sim {
             item = k < nOrd ? ent(k) : IT_NONE;
             const int island = IT_ISL(cur);
             if (((unsolved >> island) & 1ull) != 0ull) {
-              const bool ok = (cur & IT_GEN) != 0u ? solvePositionGeneralNI(*this, genSlot(kc))
-                                                   : solvePositionSimple(kc, cur);
+              const bool ok = (cur & IT_FAST) != 0u ? solvePositionFast(kc, cur)
+                              : ((cur & IT_GEN) != 0u ? solvePositionGeneralNI(*this, genSlot(kc))
+                                                      : solvePositionSimple(kc, cur));
               if (!ok) bad |= 1ull << island;
             }
           }
