@@ -74,8 +74,20 @@ class KilobotsVecEnv:
         st = self.batch.episode_stats()
         return {n: st[:, i] for i, n in enumerate(abi.EPISODE_STAT_NAMES)}
 
+    def use_device_sampler(self, configuration, seed=0):
+        """Attach a `YamlSceneSampler` for this batch's Yaml configuration: `reset_done` then draws fresh scenes
+        on the device (objects / light / kilobots as yaml_kilobots_env.py:194-198,256-283,327-354)."""
+        from .yaml_sampler import YamlSceneSampler
+        self.sampler = YamlSceneSampler(configuration, self.num_envs, device=self.batch.device, seed=seed)
+        if (self.sampler.M, self.sampler.N, self.sampler.L) != (self.batch.M, self.batch.N, self.batch.L):
+            raise ValueError("configuration does not match the batch (objects / kilobots / light state)")
+        return self.sampler
+
     def reset_done(self, done, body_pose=None, light_state=None):
-        """Auto-reset: rebuild only the envs whose `done` flag is set (device or host array)."""
+        """Auto-reset: rebuild only the envs whose `done` flag is set (device or host array).  Poses come from the
+        arguments, else from the attached device sampler (a fresh draw), else from the scenario's initial poses."""
+        if body_pose is None and getattr(self, "sampler", None) is not None:
+            body_pose, light_state = self.sampler.sample()
         pose = self.scenario.body_pose if body_pose is None else body_pose
         light = self.scenario.light_state if light_state is None else light_state
         self.batch.reset(pose, light, None, done)
