@@ -719,6 +719,13 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
       if (v == 4 || v == 8 || v == 16 || v == 32) lpe = v;
     }
     L.lanesPerEnv = lpe;
+#ifndef KB_NO_BANK_STAGGER
+    // stagger the lane groups of a warp over the 32 shared-memory banks: with a per-env stride of LPE (mod 32) words
+    // the groups' copies of the same field start LPE banks apart, so a word access by every lane of the warp is one
+    // wavefront instead of up to 32 / LPE (a stride of 0 mod 32 cost 30 % extra wavefronts, profiles/)
+    if (lpe < 32)
+      while (L.smemWords % 32 != lpe) L.smemWords += 4;
+#endif
   }
   h->envsPerBlock = KB_BLOCK_OF(L.lanesPerEnv) / L.lanesPerEnv;
   h->smemBytes = (size_t)h->envsPerBlock * L.smemWords * 4;
