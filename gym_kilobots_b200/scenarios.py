@@ -39,15 +39,14 @@ def _separated_gaussian(rngs, mean, std, n, lo, hi, min_dist, max_tries=200):
     E = len(rngs)
     out = np.zeros((E, n, 2))
     for e, rng in enumerate(rngs):
-        pts = []
+        pts = out[e]
         for k in range(n):
             for _ in range(max_tries):
                 p = rng.normal(scale=std, size=2) + mean[e]
                 p = np.minimum(np.maximum(p, lo), hi)
-                if all(np.hypot(*(p - q)) >= min_dist for q in pts):
+                if k == 0 or np.all(np.hypot(pts[:k, 0] - p[0], pts[:k, 1] - p[1]) >= min_dist):
                     break
-            pts.append(p)
-        out[e] = np.asarray(pts)
+            pts[k] = p
     return out
 
 
