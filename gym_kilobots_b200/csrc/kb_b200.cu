@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "kb_toi.cuh"
 #include "kb_render.cuh"
 
@@ -56,7 +58,10 @@ template <int LPE>
 __global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? (512 / KB_BLOCK32) : (KB_BLOCK_OF(LPE) > 64 ? 1 : (LPE == 16 ? KB_MINBLOCKS16 : (LPE == 4 ? KB_MINBLOCKS4 : KB_MINBLOCKS8))))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
   constexpr int EPB = KB_BLOCK_OF(LPE) / LPE;
   const int slot = threadIdx.x / LPE;
-  const int env = blockIdx.x * EPB + slot;
+  // load-sorted placement: slot idx runs env perm[idx], so that the lane groups that walk the solver in lock step
+  // (a warp, and the two warps of a block) hold environments of similar cost.  Padding slots keep their own env.
+  const int idx = blockIdx.x * EPB + slot;
+  const int env = (a.perm != nullptr && idx < a.numEnvs) ? a.perm[idx] : idx;
   const int envIn = min(env, a.numEnvs - 1);
   Sim<LPE, true> s(a.L);
   s.g.init();
@@ -256,6 +261,14 @@ struct Handle {
   double* dObsL = nullptr;
   uint8_t* dDone = nullptr;
   int32_t* dStatus = nullptr;
+  // load-sorted placement of the envs on lane groups (see kb_step)
+  int sortEvery = 0;                 // re-sort period in kb_step calls, 0 = identity placement
+  long long stepCalls = 0;
+  bool permValid = false;
+  uint32_t *dKey = nullptr, *dKeySorted = nullptr;
+  int32_t *dIota = nullptr, *dPerm = nullptr;
+  void* dSortTemp = nullptr;
+  size_t sortTempBytes = 0;
   float wall[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // table rectangle x0 y0 x1 y1, b2 units (render window)
   int32_t* dRenderIds = nullptr;
   int renderIdsCap = 0;
@@ -801,6 +814,29 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     h->dStatus = reinterpret_cast<int32_t*>(h->dOut + h->hostOff[4]);
     h->dDone = h->dOut + h->hostOff[5];
   }
+  {
+    // Environments are independent, so WHICH lane group runs an env is free.  Groups of a warp (and the warps of a
+    // block) sweep the solver in lock step -- rows = max over the groups, position sweeps = until the last group is
+    // done -- so every KB_SORT_EVERY-th step the envs are re-sorted by the load key the kernel wrote (radix sort of
+    // E 24-bit keys, cub) and the next launches place neighbours in that order together.  Results do not depend on
+    // the placement.  KB_SORT_EVERY=0 disables it.
+    h->sortEvery = 0;   // off unless KB_SORT_EVERY is set (not yet validated on the GPU)
+    if (const char* ev = getenv("KB_SORT_EVERY")) h->sortEvery = std::max(0, atoi(ev));
+    if (h->sortEvery > 0) {
+      const size_t E = (size_t)num_envs;
+      CUDA_TRY(cudaMalloc(&h->dKey, sizeof(uint32_t) * E));
+      CUDA_TRY(cudaMalloc(&h->dKeySorted, sizeof(uint32_t) * E));
+      CUDA_TRY(cudaMalloc(&h->dIota, sizeof(int32_t) * E));
+      CUDA_TRY(cudaMalloc(&h->dPerm, sizeof(int32_t) * E));
+      CUDA_TRY(cudaMemset(h->dKey, 0, sizeof(uint32_t) * E));
+      std::vector<int32_t> iota(E);
+      for (size_t i = 0; i < E; ++i) iota[i] = (int32_t)i;
+      CUDA_TRY(cudaMemcpy(h->dIota, iota.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice));
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, h->sortTempBytes, h->dKey, h->dKeySorted, h->dIota, h->dPerm,
+                                               num_envs, 0, 24));
+      CUDA_TRY(cudaMalloc(&h->dSortTemp, std::max<size_t>(h->sortTempBytes, 16)));
+    }
+  }
   h->wall[0] = s0.wall_x0; h->wall[1] = s0.wall_y0; h->wall[2] = s0.wall_x1; h->wall[3] = s0.wall_y1;
   CUDA_TRY(cudaMalloc(&h->dTask, sizeof(double) * KB_TASK_WORDS * (size_t)num_envs));
   CUDA_TRY(cudaMemset(h->dTask, 0, sizeof(double) * KB_TASK_WORDS * (size_t)num_envs));
@@ -830,6 +866,7 @@ int kb_destroy(KbHandle* hh) {
   cudaSetDevice(h->device);
   cudaFree(h->dBlobs); cudaFree(h->dEnvScene); cudaFree(h->dProxies); cudaFree(h->dBodies);
   cudaFree(h->dScenes); cudaFree(h->dLights); cudaFree(h->dAction); cudaFree(h->dOut); cudaFree(h->dTask); cudaFree(h->dRenderIds);
+  cudaFree(h->dKey); cudaFree(h->dKeySorted); cudaFree(h->dIota); cudaFree(h->dPerm); cudaFree(h->dSortTemp);
   delete h;
   return KB_OK;
 }
@@ -893,8 +930,16 @@ int kb_step(KbHandle* hh, const double* action, int32_t action_mode, float* obs_
   a.done = done;
   a.status = status;
   a.obsFlat = h->obsFlat;
+  a.perm = h->permValid ? h->dPerm : nullptr;
+  a.loadKey = h->dKey;
   KB_LAUNCH(kb_step_kernel, h, (cudaStream_t)stream, a);
   CUDA_TRY(cudaGetLastError());
+  if (h->sortEvery > 0 && (h->stepCalls++ % h->sortEvery) == 0) {
+    // placement of the following launches, from the keys this launch wrote (same stream: ordered after it)
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(h->dSortTemp, h->sortTempBytes, h->dKey, h->dKeySorted, h->dIota, h->dPerm,
+                                             h->numEnvs, 0, 24, (cudaStream_t)stream));
+    h->permValid = true;
+  }
   return KB_OK;
 }
 
