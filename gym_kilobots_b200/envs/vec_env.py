@@ -55,6 +55,9 @@ class KilobotsVecEnv:
         """Re-run `_configure_environment` of the (masked) source envs -> fresh initial poses / light states, the
         way a reference `reset()` re-samples its scene.  Only for batches built by `from_envs`; scene templates
         must not change.  Returns (body_pose [E,B,3], light_state [E,L]) for `reset` / `reset_done`."""
+        if getattr(self, "envs", None) is None:
+            raise RuntimeError("resample() needs the source env objects: build the batch with KilobotsVecEnv.from_envs "
+                               "(or attach a YamlSceneSampler with use_device_sampler)")
         sc = self.scenario
         for i, env in enumerate(self.envs):
             if mask is not None and not mask[i]:
