@@ -231,8 +231,11 @@ def run_ours(args):
     cnt1 = b.counters().astype(np.float64).sum(0)
     status = b.status.cpu().numpy()
 
-    # ---------------- end-to-end leg: public API, host buffers
-    for t in range(min(3, args.warmup)):
+    # ---------------- end-to-end leg: public API, host buffers.  Same episode and the same step indices as the
+    # device-resident leg (reset, W untimed steps through the host path, then the K timed ones), so that the two
+    # numbers differ by the host<->device path only
+    env.reset()
+    for t in range(args.warmup):
         env.step(acts_h[t])
     barrier()
     e0 = time.perf_counter()
