@@ -1458,12 +1458,31 @@ struct Sim {
       awakeMask |= (unsigned long long)g.ballot(b < B && awake(b)) << bb;
     }
     g.usync();
+    // awake bodies without a touching contact are islands of their own (b2World::Solve seeds them like any other
+    // awake body and finds nothing to add): they get their island numbers in parallel below, after the numbers of
+    // the islands lane 0 builds.  Island numbers are labels -- nothing depends on their order.
+    unsigned long long lonely;
+    {
+      unsigned long long hasC = 0ull;
+#pragma unroll 1
+      for (int bb = 0; bb < B; bb += LPE) {
+        const int b = bb + g.lane;
+        bool c = false;
+        if (b < B)
+          for (int w4 = 0; w4 < KW; w4 += 4) {
+            const uint4 m = lds_u4(wa(L.sBmask + b * KW + w4));
+            c |= (m.x | m.y | m.z | m.w) != 0u;
+          }
+        hasC |= (unsigned long long)g.ballot(c) << bb;
+      }
+      lonely = awakeMask & ~hasC;
+    }
     KB_T(2);
     // ---- lane 0: island DFS (b2World::Solve) in Box2D's order, dependency level of every constraint,
     //      rows, and the level-sorted schedule.  Slot S of bmask collects the contacts already in an island.
     if (g.lane == 0) {
       unsigned long long bflag = 0ull;
-      unsigned long long todo = awakeMask;  // awake dynamic bodies that are not in an island yet
+      unsigned long long todo = awakeMask & ~lonely;  // awake dynamic bodies with contacts, not in an island yet
       int nOrd = 0, nIslands = 0, maxL = 0;
       while (todo != 0ull) {
         const int seed = 63 - __clzll((long long)todo);  // body list order: newest (highest index) first
@@ -1544,7 +1563,11 @@ struct Sim {
       misc(4) = (uint32_t)nGen;
     }
     g.usync();
-    const int nOrd = (int)misc(0), nRows = (int)misc(1), nIslands = (int)misc(2);
+    const int nOrd = (int)misc(0), nRows = (int)misc(1), nIslDfs = (int)misc(2);
+    const int nIslands = nIslDfs + __popcll(lonely);
+#pragma unroll 1
+    for (int b = g.lane; b < B; b += LPE)
+      if (((lonely >> b) & 1ull) != 0ull) isl(b) = nIslDfs + __popcll(lonely & ((1ull << b) - 1ull));
     const int nRowsU = g.umax(nRows);  // warp-uniform row count: the groups of a warp sweep their rows in lock step
     {
       const int nGen = (int)misc(4);
