@@ -25,11 +25,13 @@
 namespace kb {
 
 // ----------------------------------------------------------------------------------- kernels
-// threads per block: two warps for every lane-group width.  The warps of a block rendezvous at the phase boundaries
-// (KB_T in kb_step.cuh) and so share instruction-cache lines: with one warp per block the 4-lane kernel spent
-// 10 of 17 cycles per issue waiting for instructions (profiles/ncu_c5_r01_block32.txt; +25 % throughput at 64).
+// threads per block.  The warps of a block rendezvous at the phase boundaries (KB_T in kb_step.cuh) and so share
+// instruction-cache lines: with one warp per block the 4-lane kernel spent 10 of 17 cycles per issue waiting for
+// instructions (profiles/ncu_step_kernel_r01_c5_block32_before.txt).  Measured on C5 (2^18 envs, kilobot-steps/s):
+// 32 threads 70 M, 64 threads 114 M, 96 threads 132 M, 128 threads 139 M, 192 threads 132 M; the wider kernels are best
+// at two warps (C2: 64 threads 1.215 ms, 128 threads 1.239 ms; C3: 5.39 vs 5.55 ms).
 #ifndef KB_BLOCK4
-#define KB_BLOCK4 64
+#define KB_BLOCK4 128
 #endif
 #ifndef KB_BLOCK8
 #define KB_BLOCK8 64
