@@ -27,6 +27,8 @@ KB_STATUS_SOLVER_OVERFLOW = 4
 # task layer (extension beyond the reference, include/kb_b200.h "Task layer")
 KB_TASK_CONST, KB_TASK_OBJECT_TO_TARGET, KB_TASK_SWARM_TO_TARGET = 0, 1, 2
 KB_EPISODE_STATS = 6
+KB_REDUCED_STATS = 8
+REDUCED_STAT_NAMES = ("envs",) + ("return", "length", "position_error", "orientation_error", "success", "done_count") + ("envs_with_status",)
 EPISODE_STAT_NAMES = ("return", "length", "position_error", "orientation_error", "success", "done_count")
 
 COUNTER_NAMES = ("substeps", "contacts", "points", "levels", "pos_iters", "toi_events", "pair_tests", "islands")
@@ -135,6 +137,8 @@ PROTOTYPES = {
     "step_host": (C.c_int, [_VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "get_bodies": (C.c_int, [_VP, _VP]),
     "set_poses": (C.c_int, [_VP, _VP]),
+    "set_poses_masked": (C.c_int, [_VP, _VP, _VP]),
+    "get_status": (C.c_int, [_VP, _VP]),
     "get_contacts": (C.c_int, [_VP, _VP, _VP]),
     "get_impulses": (C.c_int, [_VP, _VP]),
     "get_counters": (C.c_int, [_VP, _VP]),
@@ -159,6 +163,7 @@ PRODUCT_ONLY = {
     "set_state": (C.c_int, [_VP, _VP]),
     "get_launch_config": (C.c_int, [_VP, C.POINTER(KbLaunchConfig)]),
     "get_host_layout": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "reduce_episode_stats": (C.c_int, [_VP, _VP, _VP]),
 }
 
 

@@ -22,6 +22,22 @@ class NativeLibraryError(RuntimeError):
     pass
 
 
+class KbStatusError(RuntimeError):
+    """An env raised a KB_STATUS_* bit: its contact / solver capacity overflowed (pairs or constraints were
+    dropped, the physics is no longer the reference's) or a pose became non-finite."""
+
+
+def describe_status(status):
+    status = np.asarray(status)
+    bad = np.flatnonzero(status != 0)
+    names = ((abi.KB_STATUS_CONTACT_OVERFLOW, "contact-list overflow"), (abi.KB_STATUS_NONFINITE, "non-finite pose"),
+             (abi.KB_STATUS_SOLVER_OVERFLOW, "solver-capacity overflow"))
+    bits = int(np.bitwise_or.reduce(status[bad])) if len(bad) else 0
+    what = ", ".join(n for b, n in names if bits & b)
+    return "%d env(s) flagged (%s), first env %d; raise max_contacts (or pass max_contacts=-1 for every proxy pair)" % (
+        len(bad), what, int(bad[0]) if len(bad) else -1)
+
+
 def build(force=False):
     """Compile csrc/kb_b200.cu for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     if force or not os.path.exists(_LIB_PATH):
@@ -165,9 +181,25 @@ class NativeBatch:
         _check(_fn["get_bodies"](self.h, _hptr(out)), "kb_get_bodies")
         return out
 
-    def set_poses(self, pose):
+    def set_poses(self, pose, body_mask=None):
+        """Body.set_pose for the bodies flagged in body_mask [E,B] (None = all)."""
         pose = np.ascontiguousarray(pose, dtype=np.float64).reshape(self.E, self.B, 3)
-        _check(_fn["set_poses"](self.h, _hptr(pose)), "kb_set_poses")
+        m = None if body_mask is None else np.ascontiguousarray(body_mask, dtype=np.uint8).reshape(self.E, self.B)
+        _check(_fn["set_poses_masked"](self.h, _hptr(pose), _hptr(m)), "kb_set_poses_masked")
+
+    def get_status(self):
+        """Sticky per-env status words (host int32 [E]; synchronises)."""
+        out = np.zeros(self.E, np.int32)
+        _check(_fn["get_status"](self.h, _hptr(out)), "kb_get_status")
+        return out
+
+    def reduce_episode_stats(self, out=None):
+        """Rank-local sums of the episode statistics as a DEVICE float64[KB_REDUCED_STATS] tensor (asynchronous):
+        the operand of the NCCL all-reduce in KilobotsVecEnv.all_reduce_episode_stats."""
+        if out is None:
+            out = self.torch.zeros(abi.KB_REDUCED_STATS, dtype=self.torch.float64, device=self.device)
+        _check(_fn["reduce_episode_stats"](self.h, C.c_void_p(out.data_ptr()), self._stream()), "kb_reduce_episode_stats")
+        return out
 
     def contacts(self):
         pairs = np.zeros((self.E, self.C, 4), np.int32)
@@ -243,7 +275,9 @@ class NativeBatch:
     def launch_config(self):
         cfg = abi.KbLaunchConfig()
         _check(_fn["get_launch_config"](self.h, C.byref(cfg)), "kb_get_launch_config")
-        return {k: int(getattr(cfg, k)) for k, _ in cfg._fields_}
+        out = {k: int(getattr(cfg, k)) for k, _ in cfg._fields_}
+        out["kernel"] = "kb_step_kernel<%d>" % out["lanes_per_env"]
+        return out
 
     def get_state(self):
         out = np.zeros((self.E, self.state_bytes_per_env), np.uint8)

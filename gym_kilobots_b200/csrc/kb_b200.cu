@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? (512 / KB_BLOCK
   const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * a.L.Pp;
   s.bc = a.bodies + (size_t)scene * a.L.Bp;
-  s.lights = a.lights;
+  s.lights = a.lights + (size_t)scene * (a.L.numLights > 0 ? a.L.numLights : 1);
   s.S = a.L.B;
 #ifdef KB_PROFILE
   s.profOut = a.prof ? a.prof + (size_t)envIn * KB_PROF_SLOTS : nullptr;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(KB_BLOCK_OF(LPE)) kb_reset_kernel(const __grid
   const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * L.Pp;
   s.bc = a.bodies + (size_t)scene * L.Bp;
-  s.lights = a.lights;
+  s.lights = a.lights + (size_t)scene * (a.L.numLights > 0 ? a.L.numLights : 1);
   s.S = L.B;
   const int lane = s.g.lane;
   for (int i = lane; i < L.stateWords; i += LPE) s.word(i) = 0u;
@@ -209,13 +209,14 @@ __global__ void __launch_bounds__(KB_BLOCK_OF(LPE)) kb_setpose_kernel(const __gr
   const int scene = a.envScene ? a.envScene[envIn] : 0;
   s.px = a.proxies + (size_t)scene * L.Pp;
   s.bc = a.bodies + (size_t)scene * L.Bp;
-  s.lights = a.lights;
+  s.lights = a.lights + (size_t)scene * (a.L.numLights > 0 ? a.L.numLights : 1);
   s.S = L.B;
   s.loadState();
   s.initScratch();
   for (int b = s.g.lane; b <= L.B; b += LPE) s.isl(b) = -1;
   s.g.sync();
   for (int b = s.g.lane; b < L.B; b += LPE) {
+    if (a.mask && !a.mask[(size_t)envIn * L.B + b]) continue;   // Body.set_pose touches this one body only
     const double* p = a.pose + ((size_t)envIn * L.B + b) * 3;
     const float x = (float)(p[0] * 25.0);
     const float y = (float)(p[1] * 25.0);
@@ -239,6 +240,35 @@ __global__ void __launch_bounds__(KB_BLOCK_OF(LPE)) kb_setpose_kernel(const __gr
   // with the saved rotation and accept p = c - q*lc (identical for every body whose xf was synchronised).
   s.synchronizeFixtures(false);
   s.storeState();
+}
+
+// Episode statistics of a rank, reduced on the device to KB_REDUCED_STATS doubles (the operand of the NCCL
+// all-reduce in KilobotsVecEnv.all_reduce_episode_stats).  One block, fixed summation tree: the result depends
+// on E only, never on scheduling.
+__global__ void __launch_bounds__(1024) kb_reduce_stats_kernel(const double* task, const float* blobs, int blobWords,
+                                                                int statusWord, int numEnvs, double* out) {
+  __shared__ double sh[KB_REDUCED_STATS][32];
+  double acc[KB_REDUCED_STATS];
+  for (int k = 0; k < KB_REDUCED_STATS; ++k) acc[k] = 0.0;
+  for (int e = threadIdx.x; e < numEnvs; e += blockDim.x) {
+    const double* ts = task + (size_t)e * KB_TASK_WORDS + 3;
+    acc[0] += 1.0;
+    for (int k = 0; k < KB_EPISODE_STATS; ++k) acc[1 + k] += ts[k];
+    acc[7] += reinterpret_cast<const uint32_t*>(blobs)[(size_t)e * blobWords + statusWord] != 0u ? 1.0 : 0.0;
+  }
+  for (int k = 0; k < KB_REDUCED_STATS; ++k) {
+    double v = acc[k];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    for (int k = 0; k < KB_REDUCED_STATS; ++k) {
+      double v = threadIdx.x < (blockDim.x >> 5) ? sh[k][threadIdx.x] : 0.0;
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+      if (threadIdx.x == 0) out[k] = v;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------- host state
@@ -607,6 +637,16 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
         sd.position_iterations != s0.position_iterations || sd.dt != s0.dt || sd.damping_mode != s0.damping_mode ||
         sd.enable_toi != s0.enable_toi || sd.enable_sleep != s0.enable_sleep)
       return fail(KB_ERR_INVALID, "kb_create: scenes must agree in body/light counts and simulation constants");
+    {
+      // light components may differ between scenes (a shuffled CompositeLight, different radii): the constants are
+      // held per scene; the state / action vectors must have the same total length
+      int sl = 0, al = 0, sl0 = 0, al0 = 0;
+      for (int l = 0; l < sd.num_lights; ++l) {
+        sl += lightStateDim(sd.lights[l].type); al += lightActionDim(sd.lights[l].type);
+        sl0 += lightStateDim(s0.lights[l].type); al0 += lightActionDim(s0.lights[l].type);
+      }
+      if (sl != sl0 || al != al0) return fail(KB_ERR_INVALID, "kb_create: scenes must agree in light state / action dimensions");
+    }
     int p = sd.wall_edges;
     for (int b = 0; b < B; ++b) {
       p += sd.bodies[b].num_fixtures;
@@ -625,9 +665,13 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   L.B = B; L.M = M; L.N = N; L.P = P;
   L.Bp = B + 1;
   L.Pp = P;
-  L.Cmax = round4(max_contacts > 0 ? max_contacts : std::min(P * (P - 1) / 2, 8 * B + 32));
+  // max_contacts > 0: the caller's capacity; 0: the throughput default (8B + 32 persistent pairs, 3B + 9 touching
+  // contacts per solve: enough for separated swarms); < 0: every proxy pair, i.e. no pair can ever be dropped
+  // (what the E = 1 drop-in facade asks for: the reference's clipped-Gaussian spawn may stack kilobots)
+  const bool fullCapacity = max_contacts < 0;
+  L.Cmax = round4(max_contacts > 0 ? max_contacts : (fullCapacity ? std::max(P * (P - 1) / 2, 4) : std::min(P * (P - 1) / 2, 8 * B + 32)));
   if (L.Cmax > 65535) L.Cmax = 65532;
-  L.Kmax = round4(std::min(std::min(L.Cmax, 3 * B + 9), (int)KB_MAX_SOLVER));
+  L.Kmax = round4(std::min(fullCapacity ? L.Cmax : std::min(L.Cmax, 3 * B + 9), (int)KB_MAX_SOLVER));
   L.KW = round4((L.Kmax + 31) / 32);  // words per body mask over the touching list, padded to whole 128-bit loads
   {
     // general constraints can only arise between proxies that are not frictionless circles-with-zero-restitution
@@ -649,7 +693,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
         }
     int gen = maxObjProxies * (maxObjProxies - 1) / 2 + maxObjProxies * maxWall;
     if (!allKilobotsFrictionless) gen = L.Kmax;
-    L.Gmax = std::min(L.Kmax, std::max(8, gen));
+    L.Gmax = std::min(std::min(L.Kmax, 252), std::max(8, gen));   // general slots are 8-bit (sGs)
   }
   L.numLights = s0.num_lights;
   for (int l = 0; l < s0.num_lights; ++l) {
@@ -764,21 +808,24 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     h->hostNumProxies.push_back(allScenes[s].numProxies);
     allBodies.insert(allBodies.end(), h->hostBodies[s].begin(), h->hostBodies[s].end());
   }
-  std::vector<LightConst> lights(std::max(1, (int)s0.num_lights));
-  for (int l = 0; l < s0.num_lights; ++l) {
-    const KbLightDef& ld = s0.lights[l];
-    LightConst& lc = lights[l];
-    lc.type = ld.type;
-    lc.relative = ld.relative_actions;
-    lc.radius = ld.radius;
-    for (int k = 0; k < 2; ++k) {
-      lc.blo[k] = ld.bounds_lo[k];
-      lc.bhi[k] = ld.bounds_hi[k];
-      lc.alo[k] = ld.action_lo[k];
-      lc.ahi[k] = ld.action_hi[k];
+  const int NLp = std::max(1, (int)s0.num_lights);
+  std::vector<LightConst> lights((size_t)NLp * num_scenes);   // [scene][light]
+  std::memset(lights.data(), 0, sizeof(LightConst) * lights.size());
+  for (int s = 0; s < num_scenes; ++s)
+    for (int l = 0; l < s0.num_lights; ++l) {
+      const KbLightDef& ld = scenes[s].lights[l];
+      LightConst& lc = lights[(size_t)s * NLp + l];
+      lc.type = ld.type;
+      lc.relative = ld.relative_actions;
+      lc.radius = ld.radius;
+      for (int k = 0; k < 2; ++k) {
+        lc.blo[k] = ld.bounds_lo[k];
+        lc.bhi[k] = ld.bounds_hi[k];
+        lc.alo[k] = ld.action_lo[k];
+        lc.ahi[k] = ld.action_hi[k];
+      }
+      lc.maxVel = ld.max_velocity;
     }
-    lc.maxVel = ld.max_velocity;
-  }
 #define ALLOC_COPY(dst, vec)                                                                   \
   CUDA_TRY(cudaMalloc(&(dst), sizeof((vec)[0]) * (vec).size()));                               \
   CUDA_TRY(cudaMemcpy((dst), (vec).data(), sizeof((vec)[0]) * (vec).size(), cudaMemcpyHostToDevice));
@@ -1025,21 +1072,41 @@ int kb_get_bodies(KbHandle* hh, float* out) {
   return KB_OK;
 }
 
-int kb_set_poses(KbHandle* hh, const double* body_pose) {
+int kb_set_poses_masked(KbHandle* hh, const double* body_pose, const uint8_t* body_mask) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h || !body_pose) return fail(KB_ERR_INVALID, "kb_set_poses: null");
   CUDA_TRY(cudaSetDevice(h->device));
   double* d = nullptr;
-  const size_t bytes = sizeof(double) * (size_t)h->numEnvs * h->L.B * 3;
-  CUDA_TRY(cudaMalloc(&d, bytes));
+  uint8_t* dm = nullptr;
+  const size_t nb = (size_t)h->numEnvs * h->L.B;
+  const size_t bytes = sizeof(double) * nb * 3;
+  CUDA_TRY(cudaMalloc(&d, bytes + (body_mask ? nb : 0)));
   CUDA_TRY(cudaMemcpy(d, body_pose, bytes, cudaMemcpyHostToDevice));
+  if (body_mask) {
+    dm = reinterpret_cast<uint8_t*>(d) + bytes;
+    CUDA_TRY(cudaMemcpy(dm, body_mask, nb, cudaMemcpyHostToDevice));
+  }
   KernelArgs a;
   fillArgs(h, &a);
   a.pose = d;
+  a.mask = dm;
   KB_LAUNCH(kb_setpose_kernel, h, (cudaStream_t)0, a);
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(d);
   if (e != cudaSuccess) return fail(KB_ERR_CUDA, cudaGetErrorString(e));
+  return KB_OK;
+}
+
+int kb_set_poses(KbHandle* hh, const double* body_pose) { return kb_set_poses_masked(hh, body_pose, nullptr); }
+
+int kb_get_status(KbHandle* hh, int32_t* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !out) return fail(KB_ERR_INVALID, "kb_get_status: null");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  // header word H_STATUS of every blob: one strided copy
+  CUDA_TRY(cudaMemcpy2D(out, sizeof(int32_t), h->dBlobs + h->L.oHdr + H_STATUS, (size_t)h->L.blobWords * 4, sizeof(int32_t),
+                        (size_t)h->numEnvs, cudaMemcpyDeviceToHost));
   return KB_OK;
 }
 
@@ -1226,6 +1293,16 @@ int kb_get_episode_stats(KbHandle* hh, double* out) {
   CUDA_TRY(cudaMemcpy(ts.data(), h->dTask, sizeof(double) * ts.size(), cudaMemcpyDeviceToHost));
   for (size_t e = 0; e < E; ++e)
     for (int k = 0; k < KB_EPISODE_STATS; ++k) out[e * KB_EPISODE_STATS + k] = ts[e * KB_TASK_WORDS + 3 + k];
+  return KB_OK;
+}
+
+int kb_reduce_episode_stats(KbHandle* hh, double* out_device, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !out_device) return fail(KB_ERR_INVALID, "kb_reduce_episode_stats: null");
+  CUDA_TRY(cudaSetDevice(h->device));
+  kb_reduce_stats_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(h->dTask, h->dBlobs, h->L.blobWords, h->L.oHdr + H_STATUS,
+                                                              h->numEnvs, out_device);
+  CUDA_TRY(cudaGetLastError());
   return KB_OK;
 }
 

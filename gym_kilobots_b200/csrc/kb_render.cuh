@@ -29,7 +29,7 @@ struct Rgb {
 
 // one pixel; p in b2 units.  xf[b] = (p.x, p.y, sin, cos) of body b.
 __device__ __forceinline__ Rgb shadePixel(const RenderArgs& a, const float4* xf, const double* light, const ProxyConst* px,
-                                          const BodyConst* bc, int numProxies, int wallEdges, float x, float y) {
+                                          const BodyConst* bc, const LightConst* lights, int numProxies, int wallEdges, float x, float y) {
   const float S = 25.0f;
   Rgb c = {255.0f, 255.0f, 255.0f};                                   // table, kilobots_env.py:254-255
   // border polyline, width .003 m (:256-257), never thinner than one pixel (pygame's minimum line width)
@@ -71,13 +71,13 @@ __device__ __forceinline__ Rgb shadePixel(const RenderArgs& a, const float4* xf,
   // light (:269-270): CircularGradientLight / MomentumLight = translucent disc (255, 255, 30, alpha 150)
   int off = 0;
   for (int l = 0; l < a.L.numLights; ++l) {
-    const int type = a.lights[l].type;
+    const int type = lights[l].type;
     if (type == KB_LIGHT_LINEAR) {
       off += 1;
       continue;
     }
     const float lx = (float)(light[off] * 25.0), ly = (float)(light[off + 1] * 25.0);
-    const float R = (float)(a.lights[l].radius * 25.0);
+    const float R = (float)(lights[l].radius * 25.0);
     const float dx = x - lx, dy = y - ly;
     if (dx * dx + dy * dy <= R * R) {
       const float al = 150.0f / 255.0f, be = 1.0f - 150.0f / 255.0f;
@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(256) kb_render_kernel(const RenderArgs a) {
   const float x = a.x0 + ((float)px_ + 0.5f) * ((a.x1 - a.x0) / (float)a.width);
   const float y = a.y1 - ((float)py + 0.5f) * ((a.y1 - a.y0) / (float)a.height);   // image row 0 = top
   const Rgb c = shadePixel(a, xf, reinterpret_cast<const double*>(blob + a.L.oLight), a.proxies + (size_t)scene * a.L.Pp,
-                           a.bodies + (size_t)scene * a.L.Bp, a.scenes[scene].numProxies, a.scenes[scene].wallEdges, x, y);
+                           a.bodies + (size_t)scene * a.L.Bp, a.lights + (size_t)scene * (a.L.numLights > 0 ? a.L.numLights : 1),
+                           a.scenes[scene].numProxies, a.scenes[scene].wallEdges, x, y);
   uint8_t* o = a.out + (((size_t)img * a.height + py) * a.width + px_) * 3;
   o[0] = (uint8_t)(int)(c.r + 0.5f);
   o[1] = (uint8_t)(int)(c.g + 0.5f);

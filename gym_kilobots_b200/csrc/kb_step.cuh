@@ -78,13 +78,13 @@ struct KernelArgs {
 
 // touching-list word tl[t]: contact index | bA << 16 | bB << 22 | general << 28
 #define TL_GEN (1u << 28)
-// schedule item ent[e]: bA | bB << 6 | island << 12 | general << 18 | row << 24
+// schedule item ent[e]: bA | bB << 6 | island << 12 | general << 18 | fast << 19 | row << 22 (10 bits)
 #define IT_BA(x) ((int)((x) & 63u))
 #define IT_BB(x) ((int)(((x) >> 6) & 63u))
 #define IT_ISL(x) ((int)(((x) >> 12) & 63u))
 #define IT_GEN (1u << 18)
 #define IT_FAST (1u << 19)   /* set by storeSimple: circle manifold between two bodies whose transforms need no rotation */
-#define IT_ROW(x) ((int)((x) >> 24))
+#define IT_ROW(x) ((int)((x) >> 22))
 #define IT_NONE 0xFFFFFFFFu
 
 // All shared-memory accesses index this symbol so that the compiler emits LDS/STS with 32-bit
@@ -1513,7 +1513,7 @@ struct Sim {
                 lastLvl(bA) = l;
                 lastLvl(bB) = l;
                 lastLvl(S) = 0u;
-                ord(nOrd++) = (uint32_t)t | (l << 8) | ((uint32_t)nIslands << 16);
+                ord(nOrd++) = (uint32_t)t | (l << 10) | ((uint32_t)nIslands << 20);   // 10-bit list index and level
                 lvlTab(l) += 1u;
                 maxL = max(maxL, (int)l);
                 if (other != S && ((bflag >> other) & 1ull) == 0ull) {
@@ -1527,11 +1527,11 @@ struct Sim {
         }
         ++nIslands;
       }
-      // levels -> packed (cursor | first entry << 8 | first row << 16)
+      // levels -> packed (cursor | first entry << 10 | first row << 20)
       int e0 = 0, row = 0;
       for (int l = 1; l <= maxL; ++l) {
         const int c = (int)lvlTab(l);
-        lvlTab(l) = (uint32_t)e0 | ((uint32_t)e0 << 8) | ((uint32_t)row << 16);
+        lvlTab(l) = (uint32_t)e0 | ((uint32_t)e0 << 10) | ((uint32_t)row << 20);
         e0 += c;
         row += (c + LPE - 1) / LPE;
       }
@@ -1539,14 +1539,14 @@ struct Sim {
       int nGen = 0;
       for (int p = 0; p < nOrd; ++p) {
         const uint32_t o = ord(p);
-        const uint32_t tv = tl(o & 0xFFu);
-        const int l = (o >> 8) & 0xFF;
+        const uint32_t tv = tl(o & 0x3FFu);
+        const int l = (o >> 10) & 0x3FF;
         const uint32_t w = lvlTab(l);
         lvlTab(l) = w + 1u;
-        const int e = w & 0xFF, first = (w >> 8) & 0xFF;
-        const int r = (int)(w >> 16) + (e - first) / LPE;
+        const int e = w & 0x3FF, first = (w >> 10) & 0x3FF;
+        const int r = (int)(w >> 20) + (e - first) / LPE;
         const bool gen = (tv & TL_GEN) != 0u;
-        ent(e) = ((tv >> 16) & 0xFFFu) | ((o >> 16) << 12) | (gen ? IT_GEN : 0u) | ((uint32_t)r << 24);
+        ent(e) = ((tv >> 16) & 0xFFFu) | ((o >> 20) << 12) | (gen ? IT_GEN : 0u) | ((uint32_t)r << 22);
         entC(e) = (uint16_t)(tv & 0xFFFFu);
         if (gen) {
           if (nGen >= L.Gmax) {

@@ -178,7 +178,9 @@ class KilobotsEnv(_Base):
     def _make_batch(self, spec):
         """Factory of the batched backend (E = 1).  Product path: the CUDA library, nothing else."""
         from .. import _native
-        return _native.NativeBatch(spec, 1, device=self._device)
+        # max_contacts = -1: a slot for every proxy pair -- the reference's spawn may stack kilobots, and a single
+        # env has no throughput reason to bound its contact list
+        return _native.NativeBatch(spec, 1, max_contacts=-1, device=self._device)
 
     @staticmethod
     def _spec_key(spec):
@@ -219,7 +221,9 @@ class KilobotsEnv(_Base):
         poses = np.stack([raw[:, 8].astype(np.float64) / 25.0, raw[:, 9].astype(np.float64) / 25.0,
                           raw[:, 2].astype(np.float64)], axis=-1)
         poses[slot] = pose
-        b.set_poses(poses[None])
+        mask = np.zeros((1, len(poses)), np.uint8)
+        mask[0, slot] = 1   # b2Body::SetTransform acts on this body only (lib/body.py:67-69)
+        b.set_poses(poses[None], mask)
         self.world._mirror = b.bodies()[0]
 
     def _record_scene(self):
@@ -246,6 +250,7 @@ class KilobotsEnv(_Base):
                 self._batch.close()
             self._batch = self._make_batch(spec)
             self._batch_key = key
+            self._out = None   # host output buffers are sized for the batch they were made for
         self._scene_spec_cache = spec
         ordered = list(self._objects) + list(self._kilobots)
         self.world._slot = {id(body): i for i, body in enumerate(ordered)}
@@ -254,8 +259,16 @@ class KilobotsEnv(_Base):
         vel = None if vel is None else vel[None]
         # bodies at their poses, then one "step to resolve" (kilobots_env.py:157)
         self._batch.reset(pose, light, vel)
+        self._check_status(self._batch.get_status())
         self._sync_mirror()
         return self.get_observation()
+
+    def _check_status(self, status):
+        """Capacity overflow / non-finite poses are errors in the drop-in path: the reference (Box2D) has no
+        capacity to overflow, so a dropped pair would silently be different physics."""
+        if np.any(np.asarray(status) != 0) and not getattr(self, "allow_status_flags", False):
+            from .._native import KbStatusError, describe_status
+            raise KbStatusError(describe_status(status))
 
     def _step_batch(self, action, mode):
         out = self._out = getattr(self, '_out', None) or {
@@ -263,13 +276,15 @@ class KilobotsEnv(_Base):
             "objects": np.zeros((1, len(self._objects), 3), np.float32),
             "light": np.zeros((1, self._batch.L), np.float64),
             "reward": np.zeros(1, np.float32), "done": np.zeros(1, np.uint8), "status": np.zeros(1, np.int32)}
-        if out["kilobots"].shape[1] != len(self._kilobots) or out["objects"].shape[1] != len(self._objects):
+        if (out["kilobots"].shape[1] != len(self._kilobots) or out["objects"].shape[1] != len(self._objects)
+                or out["light"].shape[1] != self._batch.L):
             self._out = None
             return self._step_batch(action, mode)
         if hasattr(self._batch, "step_host"):
             self._batch.step_host(action, mode, out)
         else:
             out.update(self._batch.step(action, mode))
+        self._check_status(out["status"])
         return out
 
     def step(self, action: np.ndarray):

@@ -19,11 +19,14 @@ class KilobotsVecEnv:
     """
 
     def __init__(self, scenario, device=0, action_mode=abi.KB_ACTION_LIGHT, task=None, targets=None,
-                 flat_observation=False):
+                 flat_observation=False, allow_status_flags=False):
         """task / targets: optional `scene.TaskSpec` and per-env target poses [E,3] -- on-device reward, done and
         episode statistics (an extension: the reference's hooks are abstract and its in-tree envs return constants).
         flat_observation: also emit obs['flat'], the vector YamlKilobotsEnv.observation_space describes."""
         self.scenario = scenario
+        # KB_STATUS_* bits (contact / solver capacity overflow, non-finite pose) raise KbStatusError in step() and
+        # check_status() unless explicitly allowed: a dropped pair is silently different physics
+        self.allow_status_flags = allow_status_flags
         self.batch = _native.NativeBatch(scenario.scenes, scenario.body_pose.shape[0], scenario.env_scene,
                                          scenario.max_contacts, device=device)
         self.num_envs = self.batch.E
@@ -161,11 +164,41 @@ class KilobotsVecEnv:
             act = hb["action"]
             act[...] = np.asarray(action, dtype=np.float64).reshape(act.shape)
         self.batch.step_host(act, mode, hb)
+        if not self.allow_status_flags and hb["status"].any():
+            raise _native.KbStatusError(_native.describe_status(hb["status"]))
         self._sim_steps += self.scenario.scenes[0].steps_per_action
         obs = {"kilobots": hb["kilobots"], "objects": hb["objects"], "light": hb["light"]}
         if self.obs_flat is not None:
             obs["flat"] = self.obs_flat.cpu().numpy()
         return obs, hb["reward"], hb["done"].astype(bool), {"status": hb["status"]}
+
+    def check_status(self):
+        """The device path (`step_device`, `reset`) never synchronises; call this at logging cadence.  Raises
+        KbStatusError if any env carries a status bit (unless allow_status_flags), returns the int32 [E] words."""
+        st = self.batch.get_status()
+        if not self.allow_status_flags and st.any():
+            raise _native.KbStatusError(_native.describe_status(st))
+        return st
+
+    def all_reduce_episode_stats(self, group=None):
+        """Episode statistics of the WHOLE job: this rank's envs are summed on the device (kb_reduce_episode_stats,
+        one launch) and the KB_REDUCED_STATS doubles are all-reduced over the ranks (NCCL when torch.distributed is
+        initialised with the nccl backend -- the only collective of this path; environments never exchange physics).
+        Returns a dict of Python floats: env count, sums and means of the per-env statistics, flagged envs."""
+        import torch.distributed as dist
+        t = self.batch.reduce_episode_stats()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if dist.get_backend(group) != "nccl":
+                t = t.cpu()   # gloo (CPU test rigs) reduces host tensors
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        v = t.cpu().numpy()
+        out = {"sum_" + n: float(x) for n, x in zip(abi.REDUCED_STAT_NAMES, v)}
+        n = max(out["sum_envs"], 1.0)
+        out.update({"envs": int(out.pop("sum_envs")), "envs_with_status": int(out.pop("sum_envs_with_status")),
+                    "episodes_done": out["sum_done_count"]})
+        for k in ("return", "length", "position_error", "orientation_error", "success"):
+            out["mean_" + k] = out["sum_" + k] / n
+        return out
 
     def host_io_bytes(self):
         """(bytes host->device, bytes device->host) moved by one `step` call."""

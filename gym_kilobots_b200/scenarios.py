@@ -12,6 +12,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import _abi as abi
+from . import philox as PX
 from . import scene as S
 
 
@@ -47,6 +48,29 @@ def _separated_gaussian(rngs, mean, std, n, lo, hi, min_dist, max_tries=200):
                 if k == 0 or np.all(np.hypot(pts[:k, 0] - p[0], pts[:k, 1] - p[1]) >= min_dist):
                     break
             pts[k] = p
+    return out
+
+
+def _separated_gaussian_vec(rng, mean, std, n, lo, hi, min_dist, max_tries=200):
+    """Same distribution as `_separated_gaussian`, vectorised over the envs with counter-based draws (`philox.EnvRng`):
+    try t of kilobot k of env e is draw (stream KILOBOT_POS, index k * max_tries + t) of that env, whatever the batch."""
+    E = len(mean)
+    out = np.zeros((E, n, 2))
+    for k in range(n):
+        pending = np.arange(E)
+        for t in range(max_tries):
+            z0, z1 = rng.normal2(PX.STREAM_KILOBOT_POS, k * max_tries + t, sel=pending)
+            p = np.stack([z0, z1], axis=-1) * std + mean[pending]
+            p = np.minimum(np.maximum(p, lo), hi)
+            if k == 0 or t == max_tries - 1:
+                ok = np.ones(len(pending), bool)
+            else:
+                prev = out[pending, :k]
+                ok = np.all(np.hypot(prev[..., 0] - p[:, None, 0], prev[..., 1] - p[:, None, 1]) >= min_dist, axis=1)
+            out[pending[ok], k] = p[ok]
+            pending = pending[~ok]
+            if len(pending) == 0:
+                break
     return out
 
 
@@ -108,37 +132,58 @@ def c3_shapes(num_envs=8192, seed=0, env_offset=0, num_kilobots=50, **scene_kw):
     scenes = [S.SceneSpec(bodies=[o] + kb, num_objects=1, lights=[_circular_light(.2, world)], world_size=world,
                           **scene_kw) for o in objs]
     ids = np.arange(env_offset, env_offset + num_envs)
-    rngs = _rng_for(seed, ids)
+    rng = PX.EnvRng(seed, ids)
     wb = np.array([world[0] / 2, world[1] / 2])
-    light = np.stack([(r.random(2) * 2 * wb - wb) * 0.9 for r in rngs])
+    u0, u1 = rng.uniform2(PX.STREAM_LIGHT, 0)
+    light = (np.stack([u0, u1], axis=-1) * 2 * wb - wb) * 0.9
     pose = np.zeros((num_envs, 1 + num_kilobots, 3))
-    for e, r in enumerate(rngs):
-        pose[e, 0, :2] = (r.random(2) * 2 * wb - wb) * 0.7           # yaml_kilobots_env.py:194-198
-        pose[e, 0, 2] = r.random() * 2 * np.pi - np.pi
-    pose[:, 1:, :2] = _separated_gaussian(rngs, light, 0.06, num_kilobots, -wb + 0.02, wb - 0.02,
-                                          2 * S.KILOBOT_RADIUS + 1e-3)
-    for e, r in enumerate(rngs):
-        pose[e, 1:, 2] = r.random(num_kilobots) * 2 * np.pi - np.pi
+    u0, u1 = rng.uniform2(PX.STREAM_OBJECT, 0)
+    pose[:, 0, :2] = (np.stack([u0, u1], axis=-1) * 2 * wb - wb) * 0.7       # yaml_kilobots_env.py:194-198
+    pose[:, 0, 2] = rng.uniform2(PX.STREAM_OBJECT, 1)[0] * 2 * np.pi - np.pi
+    pose[:, 1:, :2] = _separated_gaussian_vec(rng, light, 0.06, num_kilobots, -wb + 0.02, wb - 0.02,
+                                              2 * S.KILOBOT_RADIUS + 1e-3)
+    pose[:, 1:, 2] = rng.uniform2(PX.STREAM_KILOBOT_ANGLE, np.arange(num_kilobots)[None, :])[0] * 2 * np.pi - np.pi
     return Scenario("C3", scenes, (ids % 3).astype(np.int32), pose, light, max_contacts=320)
 
 
 def c5_small(num_envs=1 << 20, seed=0, env_offset=0, **scene_kw):
-    """C5: 4 kilobots + 1 Quad(0.15, 0.15); throughput sweep.  Vectorised sampling (E is large)."""
+    """C5: 4 kilobots + 1 Quad(0.15, 0.15); throughput sweep.  Vectorised counter-based sampling (E is large):
+    a rank's slice of the 2^20 envs draws exactly what the same global env ids draw in a single-GPU batch."""
     world = (2.0, 1.5)
     sc = S.SceneSpec(bodies=[S.quad_body(.15, .15)] + [S.kilobot_body(abi.KB_KILOBOT_PHOTOTAXIS) for _ in range(4)],
                      num_objects=1, lights=[_circular_light(.2, world)], world_size=world, **scene_kw)
-    rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, 1, int(env_offset)]))
+    rng = PX.EnvRng(seed, np.arange(env_offset, env_offset + num_envs))
     wb = np.array([world[0] / 2, world[1] / 2])
-    light = (rng.random((num_envs, 2)) * 2 * wb - wb) * 0.9
-    # kilobots on a jittered 2x2 block around the light: separated by construction
-    base = np.array([(-.02, -.02), (.02, -.02), (-.02, .02), (.02, .02)])
-    jit = rng.uniform(-.002, .002, size=(num_envs, 4, 2))
+    u0, u1 = rng.uniform2(PX.STREAM_LIGHT, 0)
+    light = (np.stack([u0, u1], axis=-1) * 2 * wb - wb) * 0.9
     pose = np.zeros((num_envs, 5, 3))
-    pose[:, 0, :2] = (rng.random((num_envs, 2)) * 2 * wb - wb) * 0.7
-    pose[:, 0, 2] = rng.random(num_envs) * 2 * np.pi - np.pi
-    pose[:, 1:, :2] = np.minimum(np.maximum(light[:, None, :] + base[None] + jit, -wb + 0.02), wb - 0.02)
-    pose[:, 1:, 2] = rng.random((num_envs, 4)) * 2 * np.pi - np.pi
+    u0, u1 = rng.uniform2(PX.STREAM_OBJECT, 0)
+    pose[:, 0, :2] = (np.stack([u0, u1], axis=-1) * 2 * wb - wb) * 0.7
+    pose[:, 0, 2] = rng.uniform2(PX.STREAM_OBJECT, 1)[0] * 2 * np.pi - np.pi
+    # SURVEY 8(d): kilobots ~ N(L0, 0.03^2), clipped, rejection-separated (yaml_kilobots_env.py:346-352)
+    pose[:, 1:, :2] = _separated_gaussian_vec(rng, light, 0.03, 4, -wb + 0.02, wb - 0.02, 2 * S.KILOBOT_RADIUS + 1e-3)
+    pose[:, 1:, 2] = rng.uniform2(PX.STREAM_KILOBOT_ANGLE, np.arange(4)[None, :])[0] * 2 * np.pi - np.pi
     return Scenario("C5", [sc], None, pose, light, max_contacts=32)
+
+
+def c4_swarm(num_envs=256, seed=0, env_offset=0, side=32, **scene_kw):
+    """C4: side^2 PhototaxisKilobots on a side x side lattice of pitch 0.036 m centred at the origin,
+    U(+-0.001 m) jitter, headings U(-pi, pi); one CircularGradientLight of radius 0.8 m at the origin and the zero
+    action, so the whole swarm pushes inward: dense persistent contacts (large-swarm tier, grid broadphase)."""
+    world = (2.0, 1.5)
+    n = side * side
+    sc = S.SceneSpec(bodies=[S.kilobot_body(abi.KB_KILOBOT_PHOTOTAXIS) for _ in range(n)], num_objects=0,
+                     lights=[_circular_light(.8, world)], world_size=world, **scene_kw)
+    rng = PX.EnvRng(seed, np.arange(env_offset, env_offset + num_envs))
+    g = (np.arange(side) - (side - 1) / 2.0) * 0.036
+    lattice = np.stack(np.meshgrid(g, g, indexing="xy"), axis=-1).reshape(n, 2)
+    idx = np.arange(n)[None, :]
+    j0, j1 = rng.uniform2(PX.STREAM_KILOBOT_POS, idx)
+    pose = np.zeros((num_envs, n, 3))
+    pose[:, :, :2] = lattice[None] + (np.stack([j0, j1], axis=-1) * 2.0 - 1.0) * 0.001
+    pose[:, :, 2] = rng.uniform2(PX.STREAM_KILOBOT_ANGLE, idx)[0] * 2 * np.pi - np.pi
+    light = np.zeros((num_envs, 2))
+    return Scenario("C4", [sc], None, pose, light, max_contacts=0)
 
 
 def from_envs(envs, name="from_envs"):

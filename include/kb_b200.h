@@ -152,7 +152,10 @@ typedef struct KbDims {
  * Create a batch of num_envs environments.  scenes[num_scenes] are the distinct scene templates,
  * env_scene[num_envs] (host, may be NULL = all scene 0) picks one per env.  All scenes must agree
  * in num_bodies, num_objects, lights and simulation constants; only fixtures may differ.
- * max_contacts <= 0 picks a default.  device = CUDA ordinal.
+ * max_contacts > 0: capacity of the persistent contact list per env; 0: the throughput default (8B + 32 pairs,
+ * 3B + 9 touching contacts per solve -- ample for separated swarms; overflow sets KB_STATUS_* bits); < 0: one
+ * slot for every proxy pair, so that no pair is ever dropped (the E = 1 drop-in facade: the reference's clipped
+ * Gaussian spawn, yaml_kilobots_env.py:346-352, may stack kilobots on top of each other).  device = CUDA ordinal.
  */
 int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_scene,
               int32_t num_envs, int32_t max_contacts, int32_t device, KbHandle** out);
@@ -200,6 +203,12 @@ int kb_step_host(KbHandle* h, const double* action, int32_t action_mode, float* 
 int kb_get_bodies(KbHandle* h, float* out);
 /* overwrite poses like Body.set_pose (lib/body.py:67-69 -> b2Body::SetTransform): f64[E,B,3] SI units */
 int kb_set_poses(KbHandle* h, const double* body_pose);
+/* the same for the bodies whose flag in body_mask (host u8[E,B], NULL = all) is set: Body.set_pose transforms ONE
+   body and leaves every other body's sweep and proxies alone */
+int kb_set_poses_masked(KbHandle* h, const double* body_pose, const uint8_t* body_mask);
+/* per-env status word (KB_STATUS_* bits, sticky until the env is reset): host i32[E].  Also set by kb_reset's
+   settle step, which kb_step's status output does not cover */
+int kb_get_status(KbHandle* h, int32_t* out);
 /* persistent contact list in Box2D world-list order (newest first):
    pairs i32[E,max_contacts,4] = (proxyA, proxyB, touching, pointCount), count i32[E] */
 int kb_get_contacts(KbHandle* h, int32_t* pairs, int32_t* count);
@@ -265,6 +274,12 @@ typedef struct KbTaskDef {
 /* target: host f64[E,3] = (x m, y m, theta rad) per env; NULL keeps the current targets (zeros initially) */
 int kb_set_task(KbHandle* h, const KbTaskDef* task, const double* target);
 int kb_get_episode_stats(KbHandle* h, double* out /* host f64[E,KB_EPISODE_STATS] */);
+/* The rank-local half of "NCCL used only to all-reduce episode statistics" (BASELINE.json north_star; the reference's
+   per-env hook is get_info, kilobots_env.py:130-131): sums over this handle's envs, written to a DEVICE buffer of
+   KB_REDUCED_STATS doubles on `stream` (one block, fixed summation order), ready for ncclAllReduce(sum):
+   [0] envs, [1..6] sums of the KB_EP_* statistics, [7] envs whose status word is non-zero. */
+#define KB_REDUCED_STATS 8
+int kb_reduce_episode_stats(KbHandle* h, double* out_device, void* stream);
 /* device f32[E, 2N + L + 4M] written by every following kb_step (NULL unbinds); see kb_flat_observation_dim */
 int kb_bind_flat_observation(KbHandle* h, float* obs_flat);
 int kb_flat_observation_dim(const KbHandle* h);

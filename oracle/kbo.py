@@ -120,9 +120,15 @@ class OracleBatch:
         self.fn["get_bodies"](self.h, _ptr(out))
         return out
 
-    def set_poses(self, pose):
+    def set_poses(self, pose, body_mask=None):
         pose = np.ascontiguousarray(pose, dtype=np.float64).reshape(self.E, self.B, 3)
-        self.fn["set_poses"](self.h, _ptr(pose))
+        m = None if body_mask is None else np.ascontiguousarray(body_mask, dtype=np.uint8).reshape(self.E, self.B)
+        self.fn["set_poses_masked"](self.h, _ptr(pose), _ptr(m))
+
+    def get_status(self):
+        out = np.zeros(self.E, np.int32)
+        self.fn["get_status"](self.h, _ptr(out))
+        return out
 
     def contacts(self):
         pairs = np.zeros((self.E, self.C, 4), np.int32)

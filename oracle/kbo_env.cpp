@@ -490,7 +490,11 @@ int kbo_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env
   }
   h->numProxies = maxP;
   // same default and rounding as the product library (kb_create): min(P(P-1)/2, 8B+32), up to a multiple of 4
-  h->maxContacts = ((max_contacts > 0 ? max_contacts : std::min(maxP * (maxP - 1) / 2, 8 * h->numBodies + 32)) + 3) & ~3;
+  // same capacity rule as kb_create: > 0 the caller's, 0 the throughput default, < 0 every proxy pair
+  h->maxContacts = ((max_contacts > 0 ? max_contacts
+                                      : (max_contacts < 0 ? std::max(maxP * (maxP - 1) / 2, 4)
+                                                          : std::min(maxP * (maxP - 1) / 2, 8 * h->numBodies + 32))) + 3) & ~3;
+  if (h->maxContacts > 65535) h->maxContacts = 65532;
   ComputeMotorConstants(h, 1. / 10);
   h->envs.resize(num_envs);
   for (int i = 0; i < num_envs; ++i) h->envs[i].scene = env_scene ? env_scene[i] : 0;
@@ -653,17 +657,26 @@ int kbo_get_bodies(KbHandle* hh, float* out) {
   return KB_OK;
 }
 
-int kbo_set_poses(KbHandle* hh, const double* pose) {
+int kbo_set_poses_masked(KbHandle* hh, const double* pose, const uint8_t* body_mask) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   const int B = h->numBodies;
   for (size_t i = 0; i < h->envs.size(); ++i) {
     Env& e = h->envs[i];
     for (int b = 0; b < B; ++b) {
+      if (body_mask && !body_mask[i * B + b]) continue;
       const double* p = pose + (i * B + b) * 3;
       // lib/body.py:54-61: position * _world_scale (float64) -> b2Vec2 (float32)
       e.world->SetTransform(e.bodies[b], (float)(p[0] * 25.0), (float)(p[1] * 25.0), (float)p[2]);
     }
   }
+  return KB_OK;
+}
+
+int kbo_set_poses(KbHandle* hh, const double* pose) { return kbo_set_poses_masked(hh, pose, nullptr); }
+
+int kbo_get_status(KbHandle* hh, int32_t* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  for (size_t i = 0; i < h->envs.size(); ++i) out[i] = h->envs[i].status;
   return KB_OK;
 }
 
