@@ -17,9 +17,8 @@
 #include <string>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include "kb_toi.cuh"
+#include "kb_swarm.cuh"
 #include "kb_render.cuh"
 
 namespace kb {
@@ -60,10 +59,7 @@ template <int LPE>
 __global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? (512 / KB_BLOCK32) : (KB_BLOCK_OF(LPE) > 64 ? 1 : (LPE == 16 ? KB_MINBLOCKS16 : (LPE == 4 ? KB_MINBLOCKS4 : KB_MINBLOCKS8))))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
   constexpr int EPB = KB_BLOCK_OF(LPE) / LPE;
   const int slot = threadIdx.x / LPE;
-  // load-sorted placement: slot idx runs env perm[idx], so that the lane groups that walk the solver in lock step
-  // (a warp, and the two warps of a block) hold environments of similar cost.  Padding slots keep their own env.
-  const int idx = blockIdx.x * EPB + slot;
-  const int env = (a.perm != nullptr && idx < a.numEnvs) ? a.perm[idx] : idx;
+  const int env = blockIdx.x * EPB + slot;
   const int envIn = min(env, a.numEnvs - 1);
   Sim<LPE, true> s(a.L);
   s.g.init();
@@ -293,14 +289,6 @@ struct Handle {
   double* dObsL = nullptr;
   uint8_t* dDone = nullptr;
   int32_t* dStatus = nullptr;
-  // load-sorted placement of the envs on lane groups (see kb_step)
-  int sortEvery = 0;                 // re-sort period in kb_step calls, 0 = identity placement
-  long long stepCalls = 0;
-  bool permValid = false;
-  uint32_t *dKey = nullptr, *dKeySorted = nullptr;
-  int32_t *dIota = nullptr, *dPerm = nullptr;
-  void* dSortTemp = nullptr;
-  size_t sortTempBytes = 0;
   float wall[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // table rectangle x0 y0 x1 y1, b2 units (render window)
   int32_t* dRenderIds = nullptr;
   int renderIdsCap = 0;
@@ -310,6 +298,7 @@ struct Handle {
   float* obsFlat = nullptr;  // caller-owned device buffer bound by kb_bind_flat_observation
   int envsPerBlock = 4;
   size_t smemBytes = 0;
+  SwarmLayout W = {};          // W.enabled: the large-swarm tier (kb_swarm.cuh) runs this batch
 #ifdef KB_PROFILE
   unsigned long long* dProf = nullptr;
 #endif
@@ -589,6 +578,7 @@ static int buildScene(const KbSceneDesc& sd, int Bp, int Pp, std::vector<ProxyCo
 static void fillArgs(const Handle* h, KernelArgs* a) {
   std::memset(a, 0, sizeof(*a));
   a->L = h->L;
+  a->W = h->W;
   a->blobs = h->dBlobs;
   a->envScene = h->dEnvScene;
   a->proxies = h->dProxies;
@@ -627,7 +617,21 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   const KbSceneDesc& s0 = scenes[0];
   const int B = s0.num_bodies, M = s0.num_objects, N = B - M;
   if (B < 1 || M < 0 || N < 0) return fail(KB_ERR_INVALID, "kb_create: bad body counts");
-  if (B > KB_MAX_BODIES) return fail(KB_ERR_CAPACITY, "kb_create: more than 62 bodies per env is not supported by the warp-per-env kernel");
+  // tier: the lane-group kernels (kb_step.cuh) hold up to 62 bodies; above that -- or on request (KB_FORCE_SWARM=1, used
+  // by the tests to cross-check the two tiers on the same scenes) -- the CTA-per-env swarm tier (kb_swarm.cuh)
+  bool swarm = B > KB_MAX_BODIES;
+  if (const char* ev = getenv("KB_FORCE_SWARM")) swarm = swarm || atoi(ev) != 0;
+  if (swarm) {
+    if (B > KB_SWARM_MAX_BODIES) return fail(KB_ERR_CAPACITY, "kb_create: more than 2040 bodies per env is not supported");
+    if (M != 0) return fail(KB_ERR_CAPACITY, "kb_create: the large-swarm tier (> 62 bodies per env) supports kilobots only (no pushable objects)");
+    for (int s = 0; s < num_scenes; ++s)
+      for (int b = 0; b < scenes[s].num_bodies && b < B; ++b) {
+        const KbBodyDef& bd = scenes[s].bodies[b];
+        if (bd.kind == KB_BODY_OBJECT || bd.num_fixtures != 1 || bd.fixtures[0].shape != KB_SHAPE_CIRCLE ||
+            bd.fixtures[0].friction != 0.0f || bd.fixtures[0].restitution != 0.0f || !(bd.fixtures[0].density > 0.0f))
+          return fail(KB_ERR_CAPACITY, "kb_create: the large-swarm tier needs every body to be a kilobot (one frictionless circle fixture)");
+      }
+  }
   if (s0.num_lights > KB_MAX_LIGHTS) return fail(KB_ERR_INVALID, "kb_create: too many lights");
   int P = 0;
   for (int s = 0; s < num_scenes; ++s) {
@@ -654,7 +658,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     }
     P = std::max(P, p);
   }
-  if (P > KB_MAX_PROXIES) return fail(KB_ERR_CAPACITY, "kb_create: more than 64 proxies per env is not supported");
+  if (!swarm && P > KB_MAX_PROXIES) return fail(KB_ERR_CAPACITY, "kb_create: more than 64 proxies per env is not supported");
 
   Handle* h = new Handle();
   h->device = device;
@@ -665,6 +669,96 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   L.B = B; L.M = M; L.N = N; L.P = P;
   L.Bp = B + 1;
   L.Pp = P;
+  L.numLights = s0.num_lights;
+  for (int l = 0; l < s0.num_lights; ++l) {
+    L.L += lightStateDim(s0.lights[l].type);
+    L.A += lightActionDim(s0.lights[l].type);
+  }
+  if (swarm) {
+    SwarmLayout& W = h->W;
+    W.enabled = 1;
+    L.Cmax = round4(max_contacts > 0 ? max_contacts : std::min(P * (P - 1) / 2, 8 * B + 32));
+    if (L.Cmax > 65532) L.Cmax = 65532;                         // 16-bit contact indices in the schedule
+    L.Kmax = round4(std::min(L.Cmax, 3 * B + 32));
+    L.Gmax = 0;
+    L.KW = 0;
+    W.movedWords = round4((P + 31) / 32);
+    int o = 0;
+    L.oHdr = o; o += H_WORDS;
+    L.oLight = o; o += round4(2 * std::max(L.L, 1));
+    L.oPos = o; o += 4 * L.Bp;
+    L.oVel = o; o += 4 * L.Bp;
+    L.oXf = o; o += 4 * L.Bp;
+    L.oFat = o; o += 4 * L.Pp;
+    L.stateWords = round4(o);
+    W.oMoved = o; o += W.movedWords;
+    L.oCw = o; o += L.Cmax;
+    W.oCpair = o; o += L.Cmax;
+    L.oCnt = o; o += 2 * KB_NUM_COUNTERS;
+    L.oCtrl = o; o += round4(8 * std::max(N, 1));
+    L.oMan = o; o += SR_WORDS * L.Cmax;
+    W.oSweep = o; o += 4 * L.Bp;
+    L.oToi = o; o += L.Cmax;
+    L.oGen = o;
+    L.blobWords = round4(o);
+    auto al = [](int x, int a) { return (x + a - 1) / a * a; };
+    int z = 0;
+    W.zPos = z; z += 16 * L.Bp;
+    W.zVel = z; z += 16 * L.Bp;
+    W.zQ = z; z += 8 * L.Bp;
+    W.zMI = z; z += 8 * L.Bp;
+    W.zHdr = z; z += 4 * H_WORDS;
+    W.zMoved = z; z += 4 * W.movedWords;
+    z = al(z, 8);
+    W.zLight = z; z += 8 * std::max(L.L, 1);
+    W.zLc = z; z += 4 * LC_WORDS * std::max((int)s0.num_lights, 1);
+    W.zMisc = z; z += 4 * 64;
+    W.zIsl = z; z += al(2 * L.Bp, 4);
+    W.zIslState = z; z += al(L.Bp, 4);
+    W.zEnt0 = z; z += 4 * L.Kmax;
+    W.zEntC = z; z += al(2 * L.Kmax, 4);
+    W.zEntI = z; z += al(2 * L.Kmax, 4);
+    W.zRow = z; z += al(2 * (L.Kmax + 4), 4);
+    z = al(z, 16);
+    W.zScr = z;
+    const int K = L.Kmax;
+    int q = 0;
+    W.sTlC = q; q += al(2 * K, 4);
+    W.sTlB = q; q += 4 * K;
+    W.sAdj = q; q += 4 * K;
+    W.sBstart = q; q += al(2 * (L.Bp + 2), 4);
+    W.sBcur = q; q += al(2 * (L.Bp + 2), 4);
+    W.sOrd = q; q += al(2 * K, 4);
+    W.sOlvl = q; q += al(2 * K, 4);
+    W.sOisl = q; q += al(2 * K, 4);
+    W.sStack = q; q += al(2 * L.Bp, 4);
+    W.sLastLvl = q; q += al(2 * L.Bp, 4);
+    W.sCflag = q; q += al(K, 4);
+    W.sLvlCnt = q; q += al(2 * (K + 4), 4);
+    int scratch = std::max(q, 32 * K);
+    W.cWakeAt = 0;
+    scratch = std::max(scratch, 4 * L.Bp);
+    // uniform grid over the table rectangle (+2 cells of margin), cell = 0.05 m = 1.25 b2 units
+    const float cell = 1.25f;
+    W.invCell = 1.0f / cell;
+    W.gx0 = std::min(s0.wall_x0, s0.wall_x1) - 2.0f * cell;
+    W.gy0 = std::min(s0.wall_y0, s0.wall_y1) - 2.0f * cell;
+    W.gx = std::min(256, std::max(1, (int)std::ceil(std::fabs(s0.wall_x1 - s0.wall_x0) / cell) + 4));
+    W.gy = std::min(256, std::max(1, (int)std::ceil(std::fabs(s0.wall_y1 - s0.wall_y0) / cell) + 4));
+    W.hashSize = 64;
+    W.hashShift = 26;
+    while (W.hashSize < 2 * L.Cmax) { W.hashSize *= 2; W.hashShift -= 1; }
+    q = 0;
+    W.gHash = q; q += 4 * W.hashSize;
+    W.gCellStart = q; q += 4 * (W.gx * W.gy + 2);
+    W.gCellCur = q;
+    W.gSorted = q; q += al(2 * L.Pp, 4);
+    W.gPcnt = q; q += 4 * L.Pp;
+    scratch = std::max(scratch, q);
+    W.smemBytes = al(W.zScr + scratch, 16);
+    L.lanesPerEnv = KB_SWARM_THREADS;
+    L.smemWords = W.smemBytes / 4;
+  } else {
   // max_contacts > 0: the caller's capacity; 0: the throughput default (8B + 32 persistent pairs, 3B + 9 touching
   // contacts per solve: enough for separated swarms); < 0: every proxy pair, i.e. no pair can ever be dropped
   // (what the E = 1 drop-in facade asks for: the reference's clipped-Gaussian spawn may stack kilobots)
@@ -694,11 +788,6 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     int gen = maxObjProxies * (maxObjProxies - 1) / 2 + maxObjProxies * maxWall;
     if (!allKilobotsFrictionless) gen = L.Kmax;
     L.Gmax = std::min(std::min(L.Kmax, 252), std::max(8, gen));   // general slots are 8-bit (sGs)
-  }
-  L.numLights = s0.num_lights;
-  for (int l = 0; l < s0.num_lights; ++l) {
-    L.L += lightStateDim(s0.lights[l].type);
-    L.A += lightActionDim(s0.lights[l].type);
   }
   int o = 0;
   L.oHdr = o; o += H_WORDS;
@@ -747,6 +836,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   o += L.recWords;
   L.sMisc = o; o += 8;
   L.smemWords = round4(o);
+  }
   L.stepsPerAction = s0.steps_per_action;
   L.velIters = s0.velocity_iterations;
   L.posIters = s0.position_iterations;
@@ -771,7 +861,10 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     L.transLeft[1] = (float)((legRight[1] - (s * legRight[0] + c * legRight[1])) * 25.0);
     L.omegaLeft = (float)av;
   }
-  {
+  if (swarm) {
+    h->envsPerBlock = 1;
+    h->smemBytes = (size_t)h->W.smemBytes;
+  } else {
     int lpe = B <= 6 ? 4 : (B <= 24 ? 8 : (B <= 40 ? 16 : 32));
     if (const char* ev = getenv("KB_LANES_PER_ENV")) {
       const int v = atoi(ev);
@@ -785,9 +878,9 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     if (lpe < 32)
       while (L.smemWords % 32 != lpe) L.smemWords += 4;
 #endif
+    h->envsPerBlock = KB_BLOCK_OF(L.lanesPerEnv) / L.lanesPerEnv;
+    h->smemBytes = (size_t)h->envsPerBlock * L.smemWords * 4;
   }
-  h->envsPerBlock = KB_BLOCK_OF(L.lanesPerEnv) / L.lanesPerEnv;
-  h->smemBytes = (size_t)h->envsPerBlock * L.smemWords * 4;
   if (h->smemBytes > (size_t)prop.sharedMemPerBlockOptin) {
     delete h;
     return fail(KB_ERR_CAPACITY, "kb_create: per-env shared-memory image too large; lower max_contacts");
@@ -863,29 +956,6 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     h->dStatus = reinterpret_cast<int32_t*>(h->dOut + h->hostOff[4]);
     h->dDone = h->dOut + h->hostOff[5];
   }
-  {
-    // Environments are independent, so WHICH lane group runs an env is free.  Groups of a warp (and the warps of a
-    // block) sweep the solver in lock step -- rows = max over the groups, position sweeps = until the last group is
-    // done -- so every KB_SORT_EVERY-th step the envs are re-sorted by the load key the kernel wrote (radix sort of
-    // E 24-bit keys, cub) and the next launches place neighbours in that order together.  Results do not depend on
-    // the placement.  KB_SORT_EVERY=0 disables it.
-    h->sortEvery = 0;   // off unless KB_SORT_EVERY is set (not yet validated on the GPU)
-    if (const char* ev = getenv("KB_SORT_EVERY")) h->sortEvery = std::max(0, atoi(ev));
-    if (h->sortEvery > 0) {
-      const size_t E = (size_t)num_envs;
-      CUDA_TRY(cudaMalloc(&h->dKey, sizeof(uint32_t) * E));
-      CUDA_TRY(cudaMalloc(&h->dKeySorted, sizeof(uint32_t) * E));
-      CUDA_TRY(cudaMalloc(&h->dIota, sizeof(int32_t) * E));
-      CUDA_TRY(cudaMalloc(&h->dPerm, sizeof(int32_t) * E));
-      CUDA_TRY(cudaMemset(h->dKey, 0, sizeof(uint32_t) * E));
-      std::vector<int32_t> iota(E);
-      for (size_t i = 0; i < E; ++i) iota[i] = (int32_t)i;
-      CUDA_TRY(cudaMemcpy(h->dIota, iota.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice));
-      CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, h->sortTempBytes, h->dKey, h->dKeySorted, h->dIota, h->dPerm,
-                                               num_envs, 0, 24));
-      CUDA_TRY(cudaMalloc(&h->dSortTemp, std::max<size_t>(h->sortTempBytes, 16)));
-    }
-  }
   h->wall[0] = s0.wall_x0; h->wall[1] = s0.wall_y0; h->wall[2] = s0.wall_x1; h->wall[3] = s0.wall_y1;
   CUDA_TRY(cudaMalloc(&h->dTask, sizeof(double) * KB_TASK_WORDS * (size_t)num_envs));
   CUDA_TRY(cudaMemset(h->dTask, 0, sizeof(double) * KB_TASK_WORDS * (size_t)num_envs));
@@ -898,7 +968,11 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     CUDA_TRY(cudaFuncSetAttribute(kb_reset_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));  \
     CUDA_TRY(cudaFuncSetAttribute(kb_setpose_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes)); \
     break;
-  switch (L.lanesPerEnv) {
+  if (swarm) {
+    CUDA_TRY(cudaFuncSetAttribute(kb_swarm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(kb_swarm_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(kb_swarm_setpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+  } else switch (L.lanesPerEnv) {
     KB_SET_SMEM(4)
     KB_SET_SMEM(8)
     KB_SET_SMEM(16)
@@ -915,7 +989,6 @@ int kb_destroy(KbHandle* hh) {
   cudaSetDevice(h->device);
   cudaFree(h->dBlobs); cudaFree(h->dEnvScene); cudaFree(h->dProxies); cudaFree(h->dBodies);
   cudaFree(h->dScenes); cudaFree(h->dLights); cudaFree(h->dAction); cudaFree(h->dOut); cudaFree(h->dTask); cudaFree(h->dRenderIds);
-  cudaFree(h->dKey); cudaFree(h->dKeySorted); cudaFree(h->dIota); cudaFree(h->dPerm); cudaFree(h->dSortTemp);
   delete h;
   return KB_OK;
 }
@@ -935,8 +1008,10 @@ int kb_get_dims(const KbHandle* hh, KbDims* d) {
   return KB_OK;
 }
 
-#define KB_LAUNCH(kernel, h, st, a)                                                               \
-  switch ((h)->L.lanesPerEnv) {                                                                   \
+#define KB_LAUNCH(kernel, swarmKernel, h, st, a)                                                  \
+  if ((h)->W.enabled) {                                                                           \
+    swarmKernel<<<(h)->numEnvs, KB_SWARM_THREADS, (h)->smemBytes, (st)>>>(a);                         \
+  } else switch ((h)->L.lanesPerEnv) {                                                            \
     case 4: kernel<4><<<launchGrid(h), KB_BLOCK_OF(4), (h)->smemBytes, (st)>>>(a); break;               \
     case 8: kernel<8><<<launchGrid(h), KB_BLOCK_OF(8), (h)->smemBytes, (st)>>>(a); break;               \
     case 16: kernel<16><<<launchGrid(h), KB_BLOCK_OF(16), (h)->smemBytes, (st)>>>(a); break;             \
@@ -956,7 +1031,7 @@ int kb_reset(KbHandle* hh, const uint8_t* mask, const double* body_pose, const d
   a.lightInit = light_state;
   a.kbVel = kb_velocity;
   a.status = h->dStatus;
-  KB_LAUNCH(kb_reset_kernel, h, (cudaStream_t)stream, a);
+  KB_LAUNCH(kb_reset_kernel, kb_swarm_reset_kernel, h, (cudaStream_t)stream, a);
   CUDA_TRY(cudaGetLastError());
   return KB_OK;
 }
@@ -979,16 +1054,8 @@ int kb_step(KbHandle* hh, const double* action, int32_t action_mode, float* obs_
   a.done = done;
   a.status = status;
   a.obsFlat = h->obsFlat;
-  a.perm = h->permValid ? h->dPerm : nullptr;
-  a.loadKey = h->dKey;
-  KB_LAUNCH(kb_step_kernel, h, (cudaStream_t)stream, a);
+  KB_LAUNCH(kb_step_kernel, kb_swarm_step_kernel, h, (cudaStream_t)stream, a);
   CUDA_TRY(cudaGetLastError());
-  if (h->sortEvery > 0 && (h->stepCalls++ % h->sortEvery) == 0) {
-    // placement of the following launches, from the keys this launch wrote (same stream: ordered after it)
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(h->dSortTemp, h->sortTempBytes, h->dKey, h->dKeySorted, h->dIota, h->dPerm,
-                                             h->numEnvs, 0, 24, (cudaStream_t)stream));
-    h->permValid = true;
-  }
   return KB_OK;
 }
 
@@ -1090,7 +1157,7 @@ int kb_set_poses_masked(KbHandle* hh, const double* body_pose, const uint8_t* bo
   fillArgs(h, &a);
   a.pose = d;
   a.mask = dm;
-  KB_LAUNCH(kb_setpose_kernel, h, (cudaStream_t)0, a);
+  KB_LAUNCH(kb_setpose_kernel, kb_swarm_setpose_kernel, h, (cudaStream_t)0, a);
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(d);
   if (e != cudaSuccess) return fail(KB_ERR_CUDA, cudaGetErrorString(e));
@@ -1124,8 +1191,8 @@ int kb_get_contacts(KbHandle* hh, int32_t* pairs, int32_t* count) {
       const int i = nC - 1 - k;  // world-list order: newest first
       const uint32_t info = w[L.oCw + i];
       int32_t* o = pairs + ((size_t)e * L.Cmax + k) * 4;
-      o[0] = (int32_t)CW_PA(info);
-      o[1] = (int32_t)CW_PB(info);
+      o[0] = h->W.enabled ? (int32_t)(w[h->W.oCpair + i] & 0xFFFFu) : (int32_t)CW_PA(info);
+      o[1] = h->W.enabled ? (int32_t)(w[h->W.oCpair + i] >> 16) : (int32_t)CW_PB(info);
       o[2] = (info & CI_TOUCHING) ? 1 : 0;
       o[3] = (int32_t)((info & CI_PC_MASK) >> CI_PC_SHIFT);
     }
@@ -1146,8 +1213,13 @@ int kb_get_impulses(KbHandle* hh, float* out) {
       const int i = nC - 1 - k;
       const uint32_t info = w[L.oCw + i];
       const int pc = (int)((info & CI_PC_MASK) >> CI_PC_SHIFT);
-      const uint32_t* rec = w + L.oMan + MR_WORDS * i;
       float* o = out + ((size_t)e * L.Cmax + k) * 4;
+      if (h->W.enabled) {   // swarm tier: one frictionless point per contact
+        o[0] = pc > 0 ? asf(w[L.oMan + SR_WORDS * i + SR_IMP]) : 0.0f;
+        o[1] = o[2] = o[3] = 0.0f;
+        continue;
+      }
+      const uint32_t* rec = w + L.oMan + MR_WORDS * i;
       o[0] = pc > 0 ? asf(rec[MR_P0N]) : 0.0f;
       o[1] = pc > 0 ? asf(rec[MR_P0T]) : 0.0f;
       o[2] = pc > 1 ? asf(rec[MR_P1N]) : 0.0f;
@@ -1239,7 +1311,7 @@ int kb_get_launch_config(const KbHandle* hh, KbLaunchConfig* cfg) {
   const Handle* h = reinterpret_cast<const Handle*>(hh);
   if (!h || !cfg) return fail(KB_ERR_INVALID, "kb_get_launch_config: null");
   cfg->lanes_per_env = h->L.lanesPerEnv;
-  cfg->block_threads = KB_BLOCK_OF(h->L.lanesPerEnv);
+  cfg->block_threads = h->W.enabled ? KB_SWARM_THREADS : KB_BLOCK_OF(h->L.lanesPerEnv);
   cfg->grid_blocks = launchGrid(h);
   cfg->smem_bytes_per_block = (int32_t)h->smemBytes;
   cfg->state_words_per_env = h->L.stateWords;
@@ -1326,6 +1398,7 @@ int kb_render(KbHandle* hh, const int32_t* env_ids, int32_t num_images, int32_t 
   if (!h || !env_ids || !rgb || num_images < 1 || width < 1 || height < 1)
     return fail(KB_ERR_INVALID, "kb_render: invalid arguments");
   if (num_images > 65535) return fail(KB_ERR_INVALID, "kb_render: at most 65535 images per call");
+  if (h->W.enabled) return fail(KB_ERR_CAPACITY, "kb_render: not available for the large-swarm tier");
   for (int i = 0; i < num_images; ++i)
     if (env_ids[i] < 0 || env_ids[i] >= h->numEnvs) return fail(KB_ERR_INVALID, "kb_render: env id out of range");
   CUDA_TRY(cudaSetDevice(h->device));

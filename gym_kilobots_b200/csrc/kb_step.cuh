@@ -31,6 +31,7 @@ struct TaskConst {
 
 struct KernelArgs {
   Layout L;
+  SwarmLayout W;                // large-swarm tier (kb_swarm.cuh); W.enabled == 0 for the lane-group kernels
   float* blobs;                 // [E][blobWords]
   const int32_t* envScene;      // [E]
   const ProxyConst* proxies;    // [S][Pp]
@@ -47,10 +48,6 @@ struct KernelArgs {
   float* reward;
   uint8_t* done;
   int32_t* status;
-  // load-sorted placement (kb_b200.cu kb_step): slot -> env permutation of this launch, and the per-env load key
-  // (solver levels and extra position sweeps of this env-step) the next permutation is sorted by
-  const int32_t* perm;          // [E] or null = identity
-  uint32_t* loadKey;            // [E] or null
   TaskConst task;
   double* taskState;            // [E][KB_TASK_WORDS]
   float* obsFlat;               // [E][2N + L + 4M] or null
@@ -2037,7 +2034,6 @@ struct Sim {
         if (dn) ts[3 + KB_EP_DONE_COUNT] += 1.0;
         rew = (float)r;
       }
-      if (a.loadKey) a.loadKey[env] = 8u * nLvl + 2u * (nPit - min(nPit, nIsl));
       if (a.reward) a.reward[env] = rew;
       if (a.done) a.done[env] = dn;
       if (a.status) a.status[env] = (int32_t)hdr(H_STATUS);

@@ -186,6 +186,34 @@ def c4_swarm(num_envs=256, seed=0, env_offset=0, side=32, **scene_kw):
     return Scenario("C4", [sc], None, pose, light, max_contacts=0)
 
 
+def swarm_corner(num_envs=8, n=48, seed=0, env_offset=0, kilobot_kind=abi.KB_KILOBOT_PHOTOTAXIS, light_radius=.4,
+                 spread=.05, world=(1.0, 0.5), corner=True, **scene_kw):
+    """Kilobots only (no pushable object): a swarm next to the bottom-left corner of a small table with the light
+    beyond the corner, so that it jams against two table edges (wall contacts, continuous collision, dense
+    kilobot-kilobot contacts); corner=False spreads it over the table under a small light instead (most kilobots
+    see no gradient: sleeping islands that the moving light wakes again).  Used to cross-check the large-swarm
+    tier against the lane-group kernels and the oracle."""
+    wb = np.array([world[0] / 2, world[1] / 2])
+    bounds = (-wb * 1.1, wb * 1.1)
+    act = (np.array([-1, -1]) * .01, np.array([1, 1]) * .01)
+    sc = S.SceneSpec(bodies=[S.kilobot_body(kilobot_kind) for _ in range(n)], num_objects=0,
+                     lights=[S.LightSpec(abi.KB_LIGHT_CIRCULAR, radius=light_radius, bounds=bounds, action_bounds=act)],
+                     world_size=world, **scene_kw)
+    rng = PX.EnvRng(seed, np.arange(env_offset, env_offset + num_envs))
+    u0, u1 = rng.uniform2(PX.STREAM_SWARM, 0)
+    jit = (np.stack([u0, u1], axis=-1) - 0.5) * 0.04
+    if corner:
+        centre = -wb + np.array([0.09, 0.09]) + jit
+        light = np.tile(-wb * 1.05, (num_envs, 1)) + jit
+    else:
+        centre = jit * 5.0
+        light = centre + np.array([0.1, 0.05])
+    pose = np.zeros((num_envs, n, 3))
+    pose[:, :, :2] = _separated_gaussian_vec(rng, centre, spread, n, -wb + 0.02, wb - 0.02, 2 * S.KILOBOT_RADIUS + 1e-3)
+    pose[:, :, 2] = rng.uniform2(PX.STREAM_KILOBOT_ANGLE, np.arange(n)[None, :])[0] * 2 * np.pi - np.pi
+    return Scenario("swarm-corner" if corner else "swarm-spread", [sc], None, pose, light, max_contacts=0)
+
+
 def from_envs(envs, name="from_envs"):
     """Vectorise reference-style environments: every element of `envs` is a KilobotsEnv subclass instance
     (YamlKilobotsEnv(configuration=...), QuadAssemblyKilobotsEnv(), a user's own subclass ...).  Each one's

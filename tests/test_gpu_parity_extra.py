@@ -250,24 +250,3 @@ kilobots: !KilobotsConf {num: 12, mean: light, std: .03}
     obs, _, _, _ = vec.step(acts[0])
     out = ob.step(acts[0])
     assert np.array_equal(obs["kilobots"], out["kilobots"]) and np.array_equal(vec.batch.bodies(), ob.bodies())
-
-
-def test_load_sorted_placement_does_not_change_results(native, monkeypatch):
-    """kb_step re-sorts the envs over the lane groups by their solver load (KB_SORT_EVERY); environments are
-    independent, so every placement must give bit-identical states and outputs."""
-    sc = SC.c2_quad_assembly(200, seed=11, degenerate=False)     # ragged: 200 envs on 25 blocks
-    acts = SC.random_actions(sc, sc.num_envs, 12)
-    runs = []
-    for every in ("0", "1", "3"):
-        monkeypatch.setenv("KB_SORT_EVERY", every)
-        nb = native.NativeBatch(sc.scenes, sc.num_envs, sc.env_scene, sc.max_contacts)
-        nb.reset(sc.body_pose, sc.light_state)
-        outs = [nb.step(a) for a in acts]
-        runs.append((outs, nb.bodies(), nb.contacts(), nb.impulses(), nb.counters()))
-        nb.close()
-    for outs, bodies, contacts, impulses, counters in runs[1:]:
-        for o0, o1 in zip(runs[0][0], outs):
-            assert_same_obs(o0, o1, "placement")
-        assert np.array_equal(runs[0][1], bodies) and np.array_equal(runs[0][3], impulses)
-        assert np.array_equal(runs[0][2][0], contacts[0]) and np.array_equal(runs[0][2][1], contacts[1])
-        assert np.array_equal(runs[0][4], counters)
