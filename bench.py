@@ -424,7 +424,7 @@ def run_ours(args):
             if wl == args.workload:
                 continue
             r = measure(rig, wl, envs_per_gpu(wl, world), max(5, args.steps // 2), max(3, args.warmup // 2),
-                        min(args.cpu_envs, 64))
+                        min(args.cpu_envs, 16 if wl == "c4" else 64))
             if r is not None:
                 sweep.append(r)
     if rig.rank == 0:
@@ -451,7 +451,7 @@ def main():
     ap.add_argument("--ref-envs", type=int, default=2048, help="sample size of --impl reference")
     ap.add_argument("--steady-steps", type=int, default=200,
                     help="env-steps of the steady-state leg with staggered auto-resets (0 = skip)")
-    ap.add_argument("--sweep", default="c5,c3",
+    ap.add_argument("--sweep", default="c5,c3,c4",
                     help="extra workloads measured after the headline one and reported under 'sweep' ('' = none)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -276,7 +276,8 @@ class NativeBatch:
         cfg = abi.KbLaunchConfig()
         _check(_fn["get_launch_config"](self.h, C.byref(cfg)), "kb_get_launch_config")
         out = {k: int(getattr(cfg, k)) for k, _ in cfg._fields_}
-        out["kernel"] = "kb_step_kernel<%d>" % out["lanes_per_env"]
+        out["kernel"] = ("kb_swarm_step_kernel (one CTA per env)" if out["lanes_per_env"] > 32
+                         else "kb_step_kernel<%d>" % out["lanes_per_env"])
         return out
 
     def get_state(self):

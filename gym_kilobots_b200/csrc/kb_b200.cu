@@ -725,7 +725,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     int q = 0;
     W.sTlC = q; q += al(2 * K, 4);
     W.sTlB = q; q += 4 * K;
-    W.sAdj = q; q += 4 * K;
+    W.sAdj = q; q += 8 * K;          // two packed entries (list index | other body << 16) per touching contact
     W.sBstart = q; q += al(2 * (L.Bp + 2), 4);
     W.sBcur = q; q += al(2 * (L.Bp + 2), 4);
     W.sOrd = q; q += al(2 * K, 4);
@@ -747,7 +747,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     W.gy = std::min(256, std::max(1, (int)std::ceil(std::fabs(s0.wall_y1 - s0.wall_y0) / cell) + 4));
     W.hashSize = 64;
     W.hashShift = 26;
-    while (W.hashSize < 2 * L.Cmax) { W.hashSize *= 2; W.hashShift -= 1; }
+    while (W.hashSize < L.Cmax + L.Cmax / 2) { W.hashSize *= 2; W.hashShift -= 1; }   // load factor <= 2/3 at capacity
     q = 0;
     W.gHash = q; q += 4 * W.hashSize;
     W.gCellStart = q; q += 4 * (W.gx * W.gy + 2);

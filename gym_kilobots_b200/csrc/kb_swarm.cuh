@@ -45,6 +45,19 @@ namespace kb {
 #define SW_NOISLAND 0xFFFFu
 #define SW_LONELY 0xFFFEu   /* awake body without touching contacts: an island of its own */
 
+// phase timers (only with -DKB_PROFILE; compiled out of the product library): cycles of thread 0 between marks
+#ifdef KB_PROFILE
+#define SW_T(i)                          \
+  do {                                   \
+    __syncthreads();                     \
+    const long long now_ = clock64();    \
+    tp[i] += now_ - tlast;               \
+    tlast = now_;                        \
+  } while (0)
+#else
+#define SW_T(i) do { } while (0)
+#endif
+
 struct Swarm {
   const Layout& L;
   const SwarmLayout& W;
@@ -54,9 +67,16 @@ struct Swarm {
   const BodyConst* bc;
   int tid, S, nWall;
   uint32_t nSub, nCon, nPts, nLvl, nPit, nToi, nTests, nIsl;   // thread 0's copy is flushed
+#ifdef KB_PROFILE
+  long long tp[KB_PROF_SLOTS], tlast;
+#endif
 
   __device__ __forceinline__ Swarm(const Layout& l, const SwarmLayout& w) : L(l), W(w) {
     nSub = nCon = nPts = nLvl = nPit = nToi = nTests = nIsl = 0u;
+#ifdef KB_PROFILE
+    for (int i = 0; i < KB_PROF_SLOTS; ++i) tp[i] = 0;
+    tlast = clock64();
+#endif
     sa = (uint32_t)__cvta_generic_to_shared(kb_smem);
     tid = threadIdx.x;
     S = l.B;
@@ -790,6 +810,7 @@ struct Swarm {
       K = L.Kmax;
     }
     __syncthreads();
+    SW_T(2);
     // ---- per-body lists over the touching list (CSR), each sorted ascending == Box2D's contact-edge list order
     // degree counts: bstart[b + 1] (u16) by shared-memory atomics on the containing 32-bit word
 #pragma unroll 1
@@ -826,22 +847,23 @@ struct Swarm {
     for (int t = tid; t < K; t += KB_SWARM_THREADS) {
       const uint32_t bb = lds_u32(tlB + 4u * (uint32_t)t);
       const int bA = (int)(bb & 0xFFFFu), bB = (int)(bb >> 16);
-      if (bA != S) sts_u16(adj + 2u * atomicAddU16(bcur, bA), (uint32_t)t);
-      if (bB != S) sts_u16(adj + 2u * atomicAddU16(bcur, bB), (uint32_t)t);
+      // entry = touching-list index | other body << 16
+      if (bA != S) sts_u32(adj + 4u * atomicAddU16(bcur, bA), (uint32_t)t | ((uint32_t)bB << 16));
+      if (bB != S) sts_u32(adj + 4u * atomicAddU16(bcur, bB), (uint32_t)t | ((uint32_t)bA << 16));
     }
     __syncthreads();
     uint32_t lonelyCount = 0u;
 #pragma unroll 1
     for (int b = tid; b < B; b += KB_SWARM_THREADS) {
       const int s0 = (int)lds_u16(bstart + 2u * (uint32_t)b), s1 = (int)lds_u16(bstart + 2u * (uint32_t)(b + 1));
-      for (int i = s0 + 1; i < s1; ++i) {   // insertion sort (degree <= ~8)
-        const uint32_t v = lds_u16(adj + 2u * (uint32_t)i);
+      for (int i = s0 + 1; i < s1; ++i) {   // insertion sort by list index (degree <= ~8)
+        const uint32_t v = lds_u32(adj + 4u * (uint32_t)i);
         int j = i - 1;
-        while (j >= s0 && lds_u16(adj + 2u * (uint32_t)j) > v) {
-          sts_u16(adj + 2u * (uint32_t)(j + 1), lds_u16(adj + 2u * (uint32_t)j));
+        while (j >= s0 && (lds_u32(adj + 4u * (uint32_t)j) & 0xFFFFu) > (v & 0xFFFFu)) {
+          sts_u32(adj + 4u * (uint32_t)(j + 1), lds_u32(adj + 4u * (uint32_t)j));
           --j;
         }
-        sts_u16(adj + 2u * (uint32_t)(j + 1), v);
+        sts_u32(adj + 4u * (uint32_t)(j + 1), v);
       }
       if (s1 == s0 && awake(b)) {   // an island of its own (b2World::Solve seeds it and finds nothing to add)
         isl(b) = SW_LONELY;
@@ -854,7 +876,10 @@ struct Swarm {
       lonelyCount = (uint32_t)total;
     }
     __syncthreads();
-    // ---- thread 0: island DFS (b2World::Solve) in Box2D's order + dependency level of every constraint
+    SW_T(3);
+    // ---- thread 0: island DFS (b2World::Solve) in Box2D's order + dependency level of every constraint:
+    // level = 1 + max(level of the earlier constraints that share a dynamic body); the static table never links levels.
+    // The popped body's own level stays in a register (its partners are distinct bodies in this tier).
     if (tid == 0) {
       int nOrd = 0, nIslands = 0, maxL = 0;
       for (int seed = B - 1; seed >= 0; --seed) {   // body list order: newest (highest index) first
@@ -866,32 +891,33 @@ struct Swarm {
         isl(seed) = (uint32_t)nIslands;
         while (sp > 0) {
           const int b = (int)lds_u16(stack + 2u * (uint32_t)(--sp));
-          if (!awake(b)) wake(b);
           const int s0 = (int)lds_u16(bstart + 2u * (uint32_t)b), s1 = (int)lds_u16(bstart + 2u * (uint32_t)(b + 1));
+          uint32_t lb = lds_u16(lastLvl + 2u * (uint32_t)b);
+          if (!awake(b)) wake(b);
           for (int k = s0; k < s1; ++k) {
-            const int t = (int)lds_u16(adj + 2u * (uint32_t)k);
-            if (lds_u8(cflag + (uint32_t)t) != 0u) continue;
-            sts_u8(cflag + (uint32_t)t, 1u);
-            const uint32_t bb = lds_u32(tlB + 4u * (uint32_t)t);
-            const int bA = (int)(bb & 0xFFFFu), bB = (int)(bb >> 16);
-            const int other = bA == b ? bB : bA;
-            const uint32_t lA = lds_u16(lastLvl + 2u * (uint32_t)bA), lB = lds_u16(lastLvl + 2u * (uint32_t)bB);
-            const uint32_t l = (lA > lB ? lA : lB) + 1u;
-            sts_u16(lastLvl + 2u * (uint32_t)bA, l);
-            sts_u16(lastLvl + 2u * (uint32_t)bB, l);
-            sts_u16(lastLvl + 2u * (uint32_t)S, 0u);
-            sts_u16(ordT + 2u * (uint32_t)nOrd, (uint32_t)t);
+            const uint32_t en = lds_u32(adj + 4u * (uint32_t)k);
+            const uint32_t t = en & 0xFFFFu, o = en >> 16;
+            if (lds_u8(cflag + t) != 0u) continue;
+            sts_u8(cflag + t, 1u);
+            uint32_t lo = 0u;
+            if (o != (uint32_t)S) lo = lds_u16(lastLvl + 2u * o);
+            const uint32_t l = (lb > lo ? lb : lo) + 1u;
+            lb = l;
+            sts_u16(ordT + 2u * (uint32_t)nOrd, t);
             sts_u16(ordL + 2u * (uint32_t)nOrd, l);
             sts_u16(ordI + 2u * (uint32_t)nOrd, (uint32_t)nIslands);
             ++nOrd;
-            sts_u16(lvlCnt + 2u * l, lds_u16(lvlCnt + 2u * l) + 1u);
             maxL = max(maxL, (int)l);
-            if (other != S && (uint32_t)isl(other) == SW_NOISLAND) {
-              isl(other) = (uint32_t)nIslands;
-              sts_u16(stack + 2u * (uint32_t)sp, (uint32_t)other);
-              ++sp;
+            if (o != (uint32_t)S) {
+              sts_u16(lastLvl + 2u * o, l);
+              if ((uint32_t)isl((int)o) == SW_NOISLAND) {
+                isl((int)o) = (uint32_t)nIslands;
+                sts_u16(stack + 2u * (uint32_t)sp, o);
+                ++sp;
+              }
             }
           }
+          sts_u16(lastLvl + 2u * (uint32_t)b, lb);
         }
         ++nIslands;
       }
@@ -901,9 +927,13 @@ struct Swarm {
     }
     __syncthreads();
     const int nOrd = (int)misc(0), nIslDfs = (int)misc(2), maxL = (int)misc(3);
+    SW_T(4);
     nIsl += (uint32_t)nIslDfs + lonelyCount;
     nLvl += (uint32_t)maxL;
     // ---- rows: rowStart[l] = first schedule entry of level l (exclusive scan of the level counts), then scatter
+#pragma unroll 1
+    for (int p = tid; p < nOrd; p += KB_SWARM_THREADS) atomicAddU16(lvlCnt, (int)lds_u16(ordL + 2u * (uint32_t)p));
+    __syncthreads();
     {
       int run = 0;
 #pragma unroll 1
@@ -955,22 +985,30 @@ struct Swarm {
     for (int e = tid; e < nOrd; e += KB_SWARM_THREADS) initSimple(e);
     nPts += (uint32_t)nOrd;
     __syncthreads();
+    SW_T(5);
     // ---- warm start + velocity iterations: warp 0 walks the levels
+    // (a software-pipelined variant that fetched the next level's entry, records and masses ahead was measured
+    //  slower: a single warp pays ~5 cycles per issued instruction, so instruction count, not load latency, is the cost)
     if (tid < 32) {
+      int s0 = (int)rowStart(1);
       for (int l = 1; l <= maxL; ++l) {
-        const int s0 = (int)rowStart(l), s1 = (int)rowStart(l + 1);
+        const int s1 = (int)rowStart(l + 1);
         for (int e = s0 + tid; e < s1; e += 32) warmStartSimple(e);
         __syncwarp();
+        s0 = s1;
       }
       for (int it = 0; it < L.velIters; ++it) {
+        s0 = (int)rowStart(1);
         for (int l = 1; l <= maxL; ++l) {
-          const int s0 = (int)rowStart(l), s1 = (int)rowStart(l + 1);
+          const int s1 = (int)rowStart(l + 1);
           for (int e = s0 + tid; e < s1; e += 32) solveVelocitySimple(e);
           __syncwarp();
+          s0 = s1;
         }
       }
     }
     __syncthreads();
+    SW_T(6);
 #pragma unroll 1
     for (int e = tid; e < nOrd; e += KB_SWARM_THREADS) storeSimple(e);
     // ---- integrate positions
@@ -997,13 +1035,15 @@ struct Swarm {
       vel4(b) = v;
     }
     __syncthreads();
+    SW_T(7);
     // ---- position iterations with per-island early exit (islState bit 0: still iterating, bit 1: a separation
     //      below -3 linearSlop seen in this sweep)
     nPit += (uint32_t)nIslDfs + lonelyCount;   // first iteration of every island (a lonely island is solved by it)
     for (int it = 0; it < L.posIters; ++it) {
       if (tid < 32) {
+        int s0 = (int)rowStart(1);
         for (int l = 1; l <= maxL; ++l) {
-          const int s0 = (int)rowStart(l), s1 = (int)rowStart(l + 1);
+          const int s1 = (int)rowStart(l + 1);
           for (int e = s0 + tid; e < s1; e += 32) {
             const uint32_t ei = entI(e);
             const int island = (int)(ei & 0x7FFFu);
@@ -1013,6 +1053,7 @@ struct Swarm {
             }
           }
           __syncwarp();
+          s0 = s1;
         }
       }
       __syncthreads();
@@ -1032,6 +1073,7 @@ struct Swarm {
     }
     // islState now: bit 0 set = position NOT solved.  Re-purpose: bit 1 = some body of the island is not ready to sleep
     __syncthreads();
+    SW_T(8);
     // ---- copy back: SynchronizeTransform; sleep bookkeeping
 #pragma unroll 1
     for (int b = tid; b < B; b += KB_SWARM_THREADS) {
@@ -1071,8 +1113,11 @@ struct Swarm {
       }
     }
     __syncthreads();
+    SW_T(9);
     synchronizeFixtures(-1);
+    SW_T(10);
     findNewContacts();
+    SW_T(11);
   }
 
   // shared-memory u16 / u8 atomics on the containing 32-bit word
@@ -1569,9 +1614,12 @@ struct Swarm {
   __device__ __forceinline__ void worldStep() {
     nSub += 1u;
     nCon += hdr(H_NC);
+    SW_T(0);
     collide();
+    SW_T(1);
     solve();
     if (L.enableToi) solveTOI();
+    SW_T(12);
   }
 
   // ----------------------------------------------------------------------------- outputs
@@ -1683,6 +1731,11 @@ __global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_step_kernel(cons
   }
   s.gather(a, env);
   s.storeState();
+#ifdef KB_PROFILE
+  s.tp[13] += clock64() - s.tlast;
+  if (a.prof && s.tid == 0)
+    for (int i = 0; i < KB_PROF_SLOTS; ++i) a.prof[(size_t)env * KB_PROF_SLOTS + i] = (unsigned long long)s.tp[i];
+#endif
 }
 
 __global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_reset_kernel(const __grid_constant__ KernelArgs a) {
