@@ -258,7 +258,7 @@ def measure(rig, workload, E, steps, warmup, cpu_envs, steady_steps=0, sampler=N
     env.reset()
     b = env.batch
     total = steps + warmup
-    acts_h = SC.random_actions(sc, E, total, seed=1 + rank)
+    acts_h = torch.from_numpy(SC.random_actions(sc, E, total, seed=1 + rank)).pin_memory().numpy()   # pinned host inputs
     acts_d = torch.as_tensor(acts_h, dtype=torch.float64, device=dev)
 
     # ---------------- device-resident leg
@@ -387,7 +387,8 @@ def measure(rig, workload, E, steps, warmup, cpu_envs, steady_steps=0, sampler=N
             "wall_s_timed_region": wall, "per_rank_ms": per_rank_ms, "per_rank_e2e_ms": per_rank_e2e_ms,
             "e2e": {"value": env_steps_total * N / e2e_elapsed, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h),
-                    "api": "KilobotsVecEnv.step(numpy) -> kb_step_host (pinned staging, H2D + kernel + D2H)"},
+                    "api": "KilobotsVecEnv.step(pinned numpy actions) -> kb_step_host (H2D + kernel + D2H into pinned numpy; "
+                           "large batches are pipelined in chunks on two side streams)"},
             "gpu_launches": int(steps),
             "roofline": roof,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",

@@ -125,6 +125,37 @@ class KbTaskDef(C.Structure):
     ]
 
 
+KB_SAMPLE_FIXED, KB_SAMPLE_RANDOM, KB_SAMPLE_AT_OBJECT = 0, 1, 2
+KB_SAMPLE_MEAN_LIGHT, KB_SAMPLE_MEAN_RANDOM = 1, 2
+KB_SAMPLE_MAX_OBJECTS = 16
+
+
+class KbSampleObject(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("pose", C.c_double * 3), ("extent", C.c_double)]
+
+
+class KbSampleLight(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("init", C.c_double * 2)]
+
+
+class KbSampleSpec(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64),
+        ("env_id_base", C.c_int64),
+        ("world_width", C.c_double),
+        ("world_height", C.c_double),
+        ("num_objects", C.c_int32),
+        ("num_lights", C.c_int32),
+        ("objects", C.POINTER(KbSampleObject)),
+        ("lights", C.POINTER(KbSampleLight)),
+        ("shuffle_lights", C.c_int32),
+        ("kilobot_mean_mode", C.c_int32),
+        ("perm_scene", C.POINTER(C.c_int32)),
+        ("kilobot_mean", C.c_double * 2),
+        ("kilobot_std", C.c_double),
+    ]
+
+
 # name -> (restype, argtypes); the exported symbol is prefix + name
 _VP = C.c_void_p
 PROTOTYPES = {
@@ -139,6 +170,7 @@ PROTOTYPES = {
     "set_poses": (C.c_int, [_VP, _VP]),
     "set_poses_masked": (C.c_int, [_VP, _VP, _VP]),
     "get_status": (C.c_int, [_VP, _VP]),
+    "set_env_scene": (C.c_int, [_VP, _VP]),
     "get_contacts": (C.c_int, [_VP, _VP, _VP]),
     "get_impulses": (C.c_int, [_VP, _VP]),
     "get_counters": (C.c_int, [_VP, _VP]),
@@ -164,6 +196,9 @@ PRODUCT_ONLY = {
     "get_launch_config": (C.c_int, [_VP, C.POINTER(KbLaunchConfig)]),
     "get_host_layout": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "reduce_episode_stats": (C.c_int, [_VP, _VP, _VP]),
+    "set_sampler": (C.c_int, [_VP, C.POINTER(KbSampleSpec)]),
+    "reset_sampled": (C.c_int, [_VP, _VP, _VP]),
+    "get_sampled": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
 }
 
 

@@ -193,6 +193,32 @@ class NativeBatch:
         _check(_fn["get_status"](self.h, _hptr(out)), "kb_get_status")
         return out
 
+    # ---- on-device scene sampling at reset (csrc/kb_sample.cuh)
+    def set_sampler(self, spec):
+        """spec: sampler.SceneSampler (or anything with to_abi() -> (KbSampleSpec, keep-alive))."""
+        s, keep = spec.to_abi()
+        _check(_fn["set_sampler"](self.h, C.byref(s)), "kb_set_sampler")
+        self._sampler_keep = keep
+
+    def reset_sampled(self, mask=None):
+        """kb_reset with poses / light states drawn inside the reset kernel; mask: device or host uint8 [E] or None."""
+        m = self._dev(mask, self.torch.uint8, (self.E,))
+        _check(_fn["reset_sampled"](self.h, None if m is None else C.c_void_p(m.data_ptr()), self._stream()), "kb_reset_sampled")
+        self._keep_reset = (m,)
+
+    def get_sampled(self):
+        """(body_pose [E,B,3], light_state [E,L], env_scene [E], episodes [E]) of the last sampled resets (host)."""
+        pose = np.zeros((self.E, self.B, 3), np.float64)
+        light = np.zeros((self.E, max(self.L, 1)), np.float64)
+        scene = np.zeros(self.E, np.int32)
+        ep = np.zeros(self.E, np.uint32)
+        _check(_fn["get_sampled"](self.h, _hptr(pose), _hptr(light), _hptr(scene), _hptr(ep)), "kb_get_sampled")
+        return pose, light[:, :self.L], scene, ep
+
+    def set_env_scene(self, env_scene):
+        es = np.ascontiguousarray(env_scene, dtype=np.int32).reshape(self.E)
+        _check(_fn["set_env_scene"](self.h, _hptr(es)), "kb_set_env_scene")
+
     def reduce_episode_stats(self, out=None):
         """Rank-local sums of the episode statistics as a DEVICE float64[KB_REDUCED_STATS] tensor (asynchronous):
         the operand of the NCCL all-reduce in KilobotsVecEnv.all_reduce_episode_stats."""

@@ -59,7 +59,7 @@ template <int LPE>
 __global__ void __launch_bounds__(KB_BLOCK_OF(LPE), (LPE == 32 ? (512 / KB_BLOCK32) : (KB_BLOCK_OF(LPE) > 64 ? 1 : (LPE == 16 ? KB_MINBLOCKS16 : (LPE == 4 ? KB_MINBLOCKS4 : KB_MINBLOCKS8))))) kb_step_kernel(const __grid_constant__ KernelArgs a) {
   constexpr int EPB = KB_BLOCK_OF(LPE) / LPE;
   const int slot = threadIdx.x / LPE;
-  const int env = blockIdx.x * EPB + slot;
+  const int env = a.envOffset + blockIdx.x * EPB + slot;
   const int envIn = min(env, a.numEnvs - 1);
   Sim<LPE, true> s(a.L);
   s.g.init();
@@ -110,7 +110,18 @@ __global__ void __launch_bounds__(KB_BLOCK_OF(LPE)) kb_reset_kernel(const __grid
   s.g.init();
   s.bind(slot);
   s.blob = a.blobs + (size_t)env * L.blobWords;
-  const int scene = a.envScene ? a.envScene[envIn] : 0;
+  int scene = a.envScene ? a.envScene[envIn] : 0;
+  if (a.sampler && env < a.numEnvs) {
+    // a fresh scene for this env, drawn here: counter-based, keyed by (seed, global env id, episode)
+    const uint32_t ep = a.episode[env];
+    scene = sampleScene(a.sampler, a.lights, L.numLights > 0 ? L.numLights : 1, L.B, L.M, scene,
+                        a.sampler->envIdBase + env, ep, s.g.lane, LPE, a.samplePose + (size_t)env * L.B * 3,
+                        a.sampleLight + (size_t)env * (L.L > 0 ? L.L : 1), [&]() { s.g.sync(); });
+    if (s.g.lane == 0) {
+      a.episode[env] = ep + 1u;
+      if (a.envSceneW) a.envSceneW[env] = scene;
+    }
+  }
   s.px = a.proxies + (size_t)scene * L.Pp;
   s.bc = a.bodies + (size_t)scene * L.Bp;
   s.lights = a.lights + (size_t)scene * (a.L.numLights > 0 ? a.L.numLights : 1);
@@ -299,6 +310,15 @@ struct Handle {
   int envsPerBlock = 4;
   size_t smemBytes = 0;
   SwarmLayout W = {};          // W.enabled: the large-swarm tier (kb_swarm.cuh) runs this batch
+  // kb_step_host pipeline: chunks of the batch alternate between two side streams, so that the device->host copy of
+  // one chunk overlaps the kernel of the next
+  // on-device scene sampling at reset (kb_sample.cuh)
+  SamplerConst* dSampler = nullptr;
+  double *dSamplePose = nullptr, *dSampleLight = nullptr;
+  uint32_t* dEpisode = nullptr;
+  cudaStream_t pipe[2] = {nullptr, nullptr};
+  cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
+  int hostChunks = 1;
 #ifdef KB_PROFILE
   unsigned long long* dProf = nullptr;
 #endif
@@ -979,6 +999,23 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     KB_SET_SMEM(32)
   }
 #undef KB_SET_SMEM
+  {
+    // end-to-end pipeline depth: one chunk per ~8 MB of outputs, at most 8, each a whole number of blocks and at
+    // least a few waves long (small batches -- C2's 4096 envs are ONE wave -- stay a single launch)
+    const int64_t chunkBytes = 8 << 20;
+    int nc = (int)std::min<int64_t>(8, std::max<int64_t>(1, h->hostTotal / chunkBytes));
+    const int blocks = launchGrid(h);
+    while (nc > 1 && blocks / nc < 4 * 148) --nc;
+    if (const char* ev = getenv("KB_HOST_CHUNKS")) nc = std::max(1, std::min(64, atoi(ev)));
+    h->hostChunks = nc;
+    if (nc > 1) {
+      for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->evJoin[i], cudaEventDisableTiming));
+      }
+      CUDA_TRY(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+    }
+  }
   *out = reinterpret_cast<KbHandle*>(h);
   return KB_OK;
 }
@@ -989,6 +1026,12 @@ int kb_destroy(KbHandle* hh) {
   cudaSetDevice(h->device);
   cudaFree(h->dBlobs); cudaFree(h->dEnvScene); cudaFree(h->dProxies); cudaFree(h->dBodies);
   cudaFree(h->dScenes); cudaFree(h->dLights); cudaFree(h->dAction); cudaFree(h->dOut); cudaFree(h->dTask); cudaFree(h->dRenderIds);
+  cudaFree(h->dSampler); cudaFree(h->dSamplePose); cudaFree(h->dSampleLight); cudaFree(h->dEpisode);
+  for (int i = 0; i < 2; ++i) {
+    if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
+    if (h->evJoin[i]) cudaEventDestroy(h->evJoin[i]);
+  }
+  if (h->evFork) cudaEventDestroy(h->evFork);
   delete h;
   return KB_OK;
 }
@@ -1008,15 +1051,20 @@ int kb_get_dims(const KbHandle* hh, KbDims* d) {
   return KB_OK;
 }
 
-#define KB_LAUNCH(kernel, swarmKernel, h, st, a)                                                  \
+// launches `kernel` over the envs [a.envOffset, a.envOffset + count)
+#define KB_LAUNCH_RANGE(kernel, swarmKernel, h, st, a, count)                                     \
   if ((h)->W.enabled) {                                                                           \
-    swarmKernel<<<(h)->numEnvs, KB_SWARM_THREADS, (h)->smemBytes, (st)>>>(a);                         \
-  } else switch ((h)->L.lanesPerEnv) {                                                            \
-    case 4: kernel<4><<<launchGrid(h), KB_BLOCK_OF(4), (h)->smemBytes, (st)>>>(a); break;               \
-    case 8: kernel<8><<<launchGrid(h), KB_BLOCK_OF(8), (h)->smemBytes, (st)>>>(a); break;               \
-    case 16: kernel<16><<<launchGrid(h), KB_BLOCK_OF(16), (h)->smemBytes, (st)>>>(a); break;             \
-    default: kernel<32><<<launchGrid(h), KB_BLOCK_OF(32), (h)->smemBytes, (st)>>>(a); break;             \
+    swarmKernel<<<(count), KB_SWARM_THREADS, (h)->smemBytes, (st)>>>(a);                              \
+  } else {                                                                                        \
+    const int grid_ = ((count) + (h)->envsPerBlock - 1) / (h)->envsPerBlock;                      \
+    switch ((h)->L.lanesPerEnv) {                                                                 \
+      case 4: kernel<4><<<grid_, KB_BLOCK_OF(4), (h)->smemBytes, (st)>>>(a); break;                     \
+      case 8: kernel<8><<<grid_, KB_BLOCK_OF(8), (h)->smemBytes, (st)>>>(a); break;                     \
+      case 16: kernel<16><<<grid_, KB_BLOCK_OF(16), (h)->smemBytes, (st)>>>(a); break;                   \
+      default: kernel<32><<<grid_, KB_BLOCK_OF(32), (h)->smemBytes, (st)>>>(a); break;                   \
+    }                                                                                             \
   }
+#define KB_LAUNCH(kernel, swarmKernel, h, st, a) KB_LAUNCH_RANGE(kernel, swarmKernel, h, st, a, (h)->numEnvs)
 
 int kb_reset(KbHandle* hh, const uint8_t* mask, const double* body_pose, const double* light_state,
              const double* kb_velocity, void* stream) {
@@ -1036,13 +1084,118 @@ int kb_reset(KbHandle* hh, const uint8_t* mask, const double* body_pose, const d
   return KB_OK;
 }
 
-int kb_step(KbHandle* hh, const double* action, int32_t action_mode, float* obs_kilobots, float* obs_objects,
-            double* obs_light, float* reward, uint8_t* done, int32_t* status, void* stream) {
+// ---- on-device scene sampling (include/kb_b200.h "Reset with on-device scene sampling") ------------------------
+int kb_set_sampler(KbHandle* hh, const KbSampleSpec* spec) {
   Handle* h = reinterpret_cast<Handle*>(hh);
-  if (!h) return fail(KB_ERR_INVALID, "kb_step: null handle");
-  if (action_mode != KB_ACTION_NONE && action_mode != KB_ACTION_LIGHT && action_mode != KB_ACTION_KILOBOTS)
-    return fail(KB_ERR_INVALID, "kb_step: bad action_mode");
+  if (!h || !spec) return fail(KB_ERR_INVALID, "kb_set_sampler: null");
+  const Layout& L = h->L;
+  if (spec->num_objects != L.M || spec->num_objects > KB_SAMPLE_MAX_OBJECTS)
+    return fail(KB_ERR_INVALID, "kb_set_sampler: num_objects must equal the batch's (at most 16)");
+  if (spec->num_lights != L.numLights) return fail(KB_ERR_INVALID, "kb_set_sampler: num_lights must equal the batch's");
+  if ((spec->num_objects > 0 && !spec->objects) || (spec->num_lights > 0 && !spec->lights))
+    return fail(KB_ERR_INVALID, "kb_set_sampler: missing object / light descriptions");
+  SamplerConst sc;
+  std::memset(&sc, 0, sizeof(sc));
+  sc.seedLo = (uint32_t)(spec->seed & 0xFFFFFFFFull);
+  sc.seedHi = (uint32_t)(spec->seed >> 32);
+  sc.envIdBase = spec->env_id_base;
+  sc.sizeX = spec->world_width;
+  sc.sizeY = spec->world_height;
+  sc.numObjects = spec->num_objects;
+  sc.numLights = spec->num_lights;
+  sc.meanMode = spec->kilobot_mean_mode;
+  sc.mean[0] = spec->kilobot_mean[0];
+  sc.mean[1] = spec->kilobot_mean[1];
+  sc.std = spec->kilobot_std;
+  for (int i = 0; i < spec->num_objects; ++i) {
+    sc.objMode[i] = spec->objects[i].mode;
+    for (int k = 0; k < 3; ++k) sc.objPose[i][k] = spec->objects[i].pose[k];
+    sc.objExtent[i] = spec->objects[i].extent;
+  }
+  for (int l = 0; l < spec->num_lights; ++l) {
+    sc.lightMode[l] = spec->lights[l].mode;
+    if (sc.lightMode[l] == KB_SAMPLE_AT_OBJECT && L.M == 0) return fail(KB_ERR_INVALID, "kb_set_sampler: light init 'object' without objects");
+    sc.lightInit[l][0] = spec->lights[l].init[0];
+    sc.lightInit[l][1] = spec->lights[l].init[1];
+  }
+  sc.shuffle = spec->shuffle_lights && spec->num_lights > 1;
+  if (sc.shuffle) {
+    if (!spec->perm_scene) return fail(KB_ERR_INVALID, "kb_set_sampler: shuffle_lights needs perm_scene");
+    int nperm = 1;
+    for (int q = 2; q <= spec->num_lights; ++q) nperm *= q;
+    for (int r = 0; r < nperm; ++r) {
+      if (spec->perm_scene[r] < 0 || spec->perm_scene[r] >= h->numScenes) return fail(KB_ERR_INVALID, "kb_set_sampler: perm_scene out of range");
+      sc.permScene[r] = spec->perm_scene[r];
+    }
+  }
   CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t E = (size_t)h->numEnvs;
+  if (!h->dSampler) {
+    CUDA_TRY(cudaMalloc(&h->dSampler, sizeof(SamplerConst)));
+    CUDA_TRY(cudaMalloc(&h->dSamplePose, sizeof(double) * E * L.B * 3));
+    CUDA_TRY(cudaMalloc(&h->dSampleLight, sizeof(double) * E * std::max(L.L, 1)));
+    CUDA_TRY(cudaMalloc(&h->dEpisode, sizeof(uint32_t) * E));
+  }
+  CUDA_TRY(cudaMemset(h->dEpisode, 0, sizeof(uint32_t) * E));
+  CUDA_TRY(cudaMemcpy(h->dSampler, &sc, sizeof(sc), cudaMemcpyHostToDevice));
+  if (!h->dEnvScene) {   // the reset may switch scenes: the per-env scene map becomes device state
+    CUDA_TRY(cudaMalloc(&h->dEnvScene, sizeof(int32_t) * E));
+    CUDA_TRY(cudaMemset(h->dEnvScene, 0, sizeof(int32_t) * E));
+  }
+  return KB_OK;
+}
+
+int kb_reset_sampled(KbHandle* hh, const uint8_t* mask, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(KB_ERR_INVALID, "kb_reset_sampled: null handle");
+  if (!h->dSampler) return fail(KB_ERR_INVALID, "kb_reset_sampled: no sampler (kb_set_sampler)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  KernelArgs a;
+  fillArgs(h, &a);
+  a.mask = mask;
+  a.pose = h->dSamplePose;
+  a.lightInit = h->dSampleLight;
+  a.kbVel = nullptr;
+  a.status = h->dStatus;
+  a.sampler = h->dSampler;
+  a.samplePose = h->dSamplePose;
+  a.sampleLight = h->dSampleLight;
+  a.envSceneW = h->dEnvScene;
+  a.episode = h->dEpisode;
+  KB_LAUNCH(kb_reset_kernel, kb_swarm_reset_kernel, h, (cudaStream_t)stream, a);
+  CUDA_TRY(cudaGetLastError());
+  return KB_OK;
+}
+
+int kb_get_sampled(KbHandle* hh, double* body_pose, double* light_state, int32_t* env_scene, uint32_t* episodes) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !h->dSampler) return fail(KB_ERR_INVALID, "kb_get_sampled: no sampler");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t E = (size_t)h->numEnvs;
+  if (body_pose) CUDA_TRY(cudaMemcpy(body_pose, h->dSamplePose, sizeof(double) * E * h->L.B * 3, cudaMemcpyDeviceToHost));
+  if (light_state && h->L.L > 0) CUDA_TRY(cudaMemcpy(light_state, h->dSampleLight, sizeof(double) * E * h->L.L, cudaMemcpyDeviceToHost));
+  if (env_scene) CUDA_TRY(cudaMemcpy(env_scene, h->dEnvScene, sizeof(int32_t) * E, cudaMemcpyDeviceToHost));
+  if (episodes) CUDA_TRY(cudaMemcpy(episodes, h->dEpisode, sizeof(uint32_t) * E, cudaMemcpyDeviceToHost));
+  return KB_OK;
+}
+
+int kb_set_env_scene(KbHandle* hh, const int32_t* env_scene) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !env_scene) return fail(KB_ERR_INVALID, "kb_set_env_scene: null");
+  for (int i = 0; i < h->numEnvs; ++i)
+    if (env_scene[i] < 0 || env_scene[i] >= h->numScenes) return fail(KB_ERR_INVALID, "kb_set_env_scene: scene out of range");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (!h->dEnvScene) CUDA_TRY(cudaMalloc(&h->dEnvScene, sizeof(int32_t) * (size_t)h->numEnvs));
+  CUDA_TRY(cudaMemcpy(h->dEnvScene, env_scene, sizeof(int32_t) * (size_t)h->numEnvs, cudaMemcpyHostToDevice));
+  return KB_OK;
+}
+
+static int stepRange(Handle* h, const double* action, int32_t action_mode, float* obs_kilobots, float* obs_objects,
+                     double* obs_light, float* reward, uint8_t* done, int32_t* status, int envBegin, int envCount,
+                     cudaStream_t stream) {
   KernelArgs a;
   fillArgs(h, &a);
   a.action = action_mode == KB_ACTION_NONE ? nullptr : action;
@@ -1054,9 +1207,21 @@ int kb_step(KbHandle* hh, const double* action, int32_t action_mode, float* obs_
   a.done = done;
   a.status = status;
   a.obsFlat = h->obsFlat;
-  KB_LAUNCH(kb_step_kernel, kb_swarm_step_kernel, h, (cudaStream_t)stream, a);
+  a.envOffset = envBegin;
+  KB_LAUNCH_RANGE(kb_step_kernel, kb_swarm_step_kernel, h, stream, a, envCount);
   CUDA_TRY(cudaGetLastError());
   return KB_OK;
+}
+
+int kb_step(KbHandle* hh, const double* action, int32_t action_mode, float* obs_kilobots, float* obs_objects,
+            double* obs_light, float* reward, uint8_t* done, int32_t* status, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(KB_ERR_INVALID, "kb_step: null handle");
+  if (action_mode != KB_ACTION_NONE && action_mode != KB_ACTION_LIGHT && action_mode != KB_ACTION_KILOBOTS)
+    return fail(KB_ERR_INVALID, "kb_step: bad action_mode");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return stepRange(h, action, action_mode, obs_kilobots, obs_objects, obs_light, reward, done, status, 0, h->numEnvs,
+                   (cudaStream_t)stream);
 }
 
 int kb_step_host(KbHandle* hh, const double* action, int32_t action_mode, float* obs_kilobots, float* obs_objects,
@@ -1067,6 +1232,41 @@ int kb_step_host(KbHandle* hh, const double* action, int32_t action_mode, float*
   cudaStream_t st = (cudaStream_t)stream;
   const Layout& L = h->L;
   const size_t E = (size_t)h->numEnvs;
+  if (action_mode != KB_ACTION_NONE && action_mode != KB_ACTION_LIGHT && action_mode != KB_ACTION_KILOBOTS)
+    return fail(KB_ERR_INVALID, "kb_step_host: bad action_mode");
+  if (h->hostChunks > 1) {
+    // pipelined: chunk c = H2D of its actions, kernel over its envs, D2H of its outputs, on side stream c % 2; the
+    // copies of one chunk overlap the kernel of the next.  Chunks are whole blocks; only the last one is ragged.
+    const size_t A = action_mode == KB_ACTION_KILOBOTS ? 2 * (size_t)L.N : (size_t)L.A;
+    const bool haveAct = action && action_mode != KB_ACTION_NONE;
+    const int epb = h->envsPerBlock, blocks = launchGrid(h), nc = h->hostChunks;
+    CUDA_TRY(cudaEventRecord(h->evFork, st));
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamWaitEvent(h->pipe[i], h->evFork, 0));
+    for (int c = 0; c < nc; ++c) {
+      const int b0 = (int)((int64_t)blocks * c / nc), b1 = (int)((int64_t)blocks * (c + 1) / nc);
+      const int e0 = b0 * epb, e1 = std::min(b1 * epb, h->numEnvs);
+      if (e1 <= e0) continue;
+      const size_t n = (size_t)(e1 - e0);
+      cudaStream_t s = h->pipe[c & 1];
+      if (haveAct) CUDA_TRY(cudaMemcpyAsync(h->dAction + (size_t)e0 * A, action + (size_t)e0 * A, sizeof(double) * n * A, cudaMemcpyHostToDevice, s));
+      int rc = stepRange(h, haveAct ? h->dAction : nullptr, action_mode, obs_kilobots ? h->dObsK : nullptr,
+                         obs_objects ? h->dObsO : nullptr, obs_light ? h->dObsL : nullptr, reward ? h->dReward : nullptr,
+                         done ? h->dDone : nullptr, status ? h->dStatus : nullptr, e0, e1 - e0, s);
+      if (rc != KB_OK) return rc;
+      if (obs_kilobots && L.N > 0) CUDA_TRY(cudaMemcpyAsync(obs_kilobots + (size_t)e0 * L.N * 3, h->dObsK + (size_t)e0 * L.N * 3, sizeof(float) * n * L.N * 3, cudaMemcpyDeviceToHost, s));
+      if (obs_objects && L.M > 0) CUDA_TRY(cudaMemcpyAsync(obs_objects + (size_t)e0 * L.M * 3, h->dObsO + (size_t)e0 * L.M * 3, sizeof(float) * n * L.M * 3, cudaMemcpyDeviceToHost, s));
+      if (obs_light && L.L > 0) CUDA_TRY(cudaMemcpyAsync(obs_light + (size_t)e0 * L.L, h->dObsL + (size_t)e0 * L.L, sizeof(double) * n * L.L, cudaMemcpyDeviceToHost, s));
+      if (reward) CUDA_TRY(cudaMemcpyAsync(reward + e0, h->dReward + e0, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+      if (done) CUDA_TRY(cudaMemcpyAsync(done + e0, h->dDone + e0, n, cudaMemcpyDeviceToHost, s));
+      if (status) CUDA_TRY(cudaMemcpyAsync(status + e0, h->dStatus + e0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(cudaEventRecord(h->evJoin[i], h->pipe[i]));
+      CUDA_TRY(cudaStreamWaitEvent(st, h->evJoin[i], 0));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return KB_OK;
+  }
   const double* dAct = nullptr;
   if (action && action_mode != KB_ACTION_NONE) {
     const size_t A = action_mode == KB_ACTION_KILOBOTS ? 2 * (size_t)L.N : (size_t)L.A;

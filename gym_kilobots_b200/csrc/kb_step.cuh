@@ -18,6 +18,7 @@
 // sequential sweep.
 #pragma once
 #include "kb_narrow.cuh"
+#include "kb_sample.cuh"
 
 namespace kb {
 
@@ -39,6 +40,7 @@ struct KernelArgs {
   const SceneConst* scenes;     // [S]
   const LightConst* lights;     // [numLights]
   int32_t numEnvs;
+  int32_t envOffset;             // first env of this launch (kb_step_host pipelines the batch in chunks)
   // step
   const double* action;
   int32_t actionMode;
@@ -59,6 +61,13 @@ struct KernelArgs {
   const double* pose;
   const double* lightInit;
   const double* kbVel;
+  // reset with on-device scene sampling (kb_sample.cuh): the kernel draws pose / lightInit itself into the handle's
+  // sample buffers (samplePose == pose, sampleLight == lightInit), may switch the env's scene, and counts episodes
+  const SamplerConst* sampler;
+  double* samplePose;
+  double* sampleLight;
+  int32_t* envSceneW;
+  uint32_t* episode;
 };
 
 // general-constraint record words (GR_WORDS per record, HBM/L2)

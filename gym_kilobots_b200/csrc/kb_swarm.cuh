@@ -1699,16 +1699,16 @@ struct Swarm {
 };
 
 // ----------------------------------------------------------------------------------- kernels
-__device__ __forceinline__ void swarmBind(Swarm& s, const KernelArgs& a, int env) {
+__device__ __forceinline__ void swarmBind(Swarm& s, const KernelArgs& a, int env, int sceneOverride = -1) {
   s.blob = a.blobs + (size_t)env * a.L.blobWords;
-  const int scene = a.envScene ? a.envScene[env] : 0;
+  const int scene = sceneOverride >= 0 ? sceneOverride : (a.envScene ? a.envScene[env] : 0);
   s.px = a.proxies + (size_t)scene * a.L.Pp;
   s.bc = a.bodies + (size_t)scene * a.L.Bp;
   s.nWall = __ldg(&a.scenes[scene].wallEdges);
 }
 
 __global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_step_kernel(const __grid_constant__ KernelArgs a) {
-  const int env = blockIdx.x;
+  const int env = a.envOffset + blockIdx.x;
   Swarm s(a.L, a.W);
   swarmBind(s, a, env);
   const int scene = a.envScene ? a.envScene[env] : 0;
@@ -1743,8 +1743,19 @@ __global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_reset_kernel(con
   if (a.mask && !a.mask[env]) return;
   const Layout& L = a.L;
   Swarm s(a.L, a.W);
-  swarmBind(s, a, env);
-  const int scene = a.envScene ? a.envScene[env] : 0;
+  int scene = a.envScene ? a.envScene[env] : 0;
+  if (a.sampler) {   // a fresh scene drawn on the device (kb_sample.cuh)
+    const uint32_t ep = a.episode[env];
+    scene = sampleScene(a.sampler, a.lights, L.numLights > 0 ? L.numLights : 1, L.B, L.M, scene, a.sampler->envIdBase + env, ep,
+                        s.tid, KB_SWARM_THREADS, a.samplePose + (size_t)env * L.B * 3,
+                        a.sampleLight + (size_t)env * (L.L > 0 ? L.L : 1), []() { __syncthreads(); });
+    if (s.tid == 0) {
+      a.episode[env] = ep + 1u;
+      if (a.envSceneW) a.envSceneW[env] = scene;
+    }
+    __syncthreads();
+  }
+  swarmBind(s, a, env, scene);
   const int tid = s.tid;
   uint32_t* bw = reinterpret_cast<uint32_t*>(s.blob);
   for (int i = tid; i < 2 * KB_NUM_COUNTERS; i += KB_SWARM_THREADS) bw[L.oCnt + i] = 0u;

@@ -60,7 +60,7 @@ class KilobotsVecEnv:
         must not change.  Returns (body_pose [E,B,3], light_state [E,L]) for `reset` / `reset_done`."""
         if getattr(self, "envs", None) is None:
             raise RuntimeError("resample() needs the source env objects: build the batch with KilobotsVecEnv.from_envs "
-                               "(or attach a YamlSceneSampler with use_device_sampler)")
+                               "(or use on-device sampling: KilobotsVecEnv.from_configuration)")
         sc = self.scenario
         for i, env in enumerate(self.envs):
             if mask is not None and not mask[i]:
@@ -80,20 +80,44 @@ class KilobotsVecEnv:
         st = self.batch.episode_stats()
         return {n: st[:, i] for i, n in enumerate(abi.EPISODE_STAT_NAMES)}
 
-    def use_device_sampler(self, configuration, seed=0):
-        """Attach a `YamlSceneSampler` for this batch's Yaml configuration: `reset_done` then draws fresh scenes
-        on the device (objects / light / kilobots as yaml_kilobots_env.py:194-198,256-283,327-354)."""
-        from .yaml_sampler import YamlSceneSampler
-        self.sampler = YamlSceneSampler(configuration, self.num_envs, device=self.batch.device, seed=seed)
-        if (self.sampler.M, self.sampler.N, self.sampler.L) != (self.batch.M, self.batch.N, self.batch.L):
+    @classmethod
+    def from_configuration(cls, configuration, num_envs, seed=0, env_id_base=0, device=0, **kwargs):
+        """E YamlKilobotsEnv(configuration=...) as ONE batch whose scenes are drawn on the device: objects, light(s)
+        and kilobots are re-sampled inside the reset kernel (counter-based, keyed by seed / global env id / episode),
+        like every reference reset() re-draws them (yaml_kilobots_env.py:194-198,256-283,299,327-354).
+        env_id_base: global id of this batch's env 0 (rank * num_envs), so that R ranks draw what one rank would."""
+        from .. import scenarios
+        from ..sampler import SceneSampler
+        sampler = SceneSampler(configuration, seed=seed, env_id_base=env_id_base)
+        specs = sampler.scene_specs()
+        pose, light, scene = sampler.sample_numpy(np.arange(num_envs), 0)
+        sc = scenarios.Scenario("yaml", specs, scene.astype(np.int32), pose, light)
+        vec = cls(sc, device=device, **kwargs)
+        vec.use_device_sampler(sampler)
+        return vec
+
+    def use_device_sampler(self, sampler, seed=0, env_id_base=0):
+        """Attach on-device scene sampling: `reset()` and `reset_done()` then draw fresh scenes inside the reset kernel
+        (kb_reset_sampled, one launch, no host round trip).  sampler: a `sampler.SceneSampler`, or a Yaml configuration
+        (then the batch's scenes must already be the sampler's: see `from_configuration`)."""
+        from ..sampler import SceneSampler
+        if not isinstance(sampler, SceneSampler):
+            sampler = SceneSampler(sampler, seed=seed, env_id_base=env_id_base)
+        if (sampler.M, sampler.N, sampler.light_state_dim()) != (self.batch.M, self.batch.N, self.batch.L):
             raise ValueError("configuration does not match the batch (objects / kilobots / light state)")
-        return self.sampler
+        if len(sampler.perms) > len(self.scenario.scenes):
+            raise ValueError("a shuffled composite light needs one scene template per permutation (from_configuration)")
+        self.batch.set_sampler(sampler)
+        self.sampler = sampler
+        return sampler
 
     def reset_done(self, done, body_pose=None, light_state=None):
         """Auto-reset: rebuild only the envs whose `done` flag is set (device or host array).  Poses come from the
-        arguments, else from the attached device sampler (a fresh draw), else from the scenario's initial poses."""
+        arguments, else from the attached device sampler (a fresh draw inside the reset kernel), else from the
+        scenario's initial poses."""
         if body_pose is None and getattr(self, "sampler", None) is not None:
-            body_pose, light_state = self.sampler.sample()
+            self.batch.reset_sampled(done)
+            return
         pose = self.scenario.body_pose if body_pose is None else body_pose
         light = self.scenario.light_state if light_state is None else light_state
         self.batch.reset(pose, light, None, done)
@@ -111,6 +135,10 @@ class KilobotsVecEnv:
 
     def reset(self, body_pose=None, light_state=None, kb_velocity=None, mask=None):
         """KilobotsEnv.reset for every (masked) env: rebuild bodies at the poses, one settle step."""
+        if body_pose is None and getattr(self, "sampler", None) is not None:
+            self.batch.reset_sampled(mask)    # a fresh scene per env, like every reference reset()
+            self._sim_steps = 0
+            return self.get_observation()
         pose = self.scenario.body_pose if body_pose is None else body_pose
         light = self.scenario.light_state if light_state is None else light_state
         if kb_velocity is None:
@@ -162,7 +190,11 @@ class KilobotsVecEnv:
         else:
             mode = self.action_mode
             act = hb["action"]
-            act[...] = np.asarray(action, dtype=np.float64).reshape(act.shape)
+            a = np.asarray(action)
+            if a.dtype == np.float64 and a.flags.c_contiguous and a.size == act.size:
+                act = a.reshape(act.shape)   # the caller's buffer goes to the device as it is (pin it for async copies)
+            else:
+                act[...] = np.asarray(action, dtype=np.float64).reshape(act.shape)
         self.batch.step_host(act, mode, hb)
         if not self.allow_status_flags and hb["status"].any():
             raise _native.KbStatusError(_native.describe_status(hb["status"]))

@@ -54,15 +54,20 @@ def _to_double(hi, lo):
 class EnvRng:
     """Per-env counter-based streams for a set of global env ids."""
 
-    def __init__(self, seed, env_ids):
+    def __init__(self, seed, env_ids, episode=0):
+        """episode: scalar or [E] -- the number of sampled resets the env has had (device: kb_sample.cuh)."""
         self.seed = int(seed)
         self.env = np.asarray(env_ids, dtype=np.uint64)
+        self.episode = np.broadcast_to(np.asarray(episode, dtype=np.uint64), self.env.shape)
 
     def _raw(self, stream, index, sel=None):
         env = self.env if sel is None else self.env[sel]
+        ep = self.episode if sel is None else self.episode[sel]
         idx = np.asarray(index, dtype=np.uint64)
-        env_b, idx_b = np.broadcast_arrays(env.reshape(env.shape + (1,) * (idx.ndim - 1)) if idx.ndim > 1 else env, idx)
-        return philox4x32(idx_b & _MASK, np.uint32(stream), env_b & _MASK, env_b >> np.uint64(32),
+        shp = (lambda a: a.reshape(a.shape + (1,) * (idx.ndim - 1)) if idx.ndim > 1 else a)
+        env_b, ep_b, idx_b = np.broadcast_arrays(shp(env), shp(ep), idx)
+        c1 = (np.uint64(stream) + (ep_b << np.uint64(8))) & _MASK
+        return philox4x32(idx_b & _MASK, c1, env_b & _MASK, env_b >> np.uint64(32),
                           np.uint32(self.seed & 0xFFFFFFFF), np.uint32((self.seed >> 32) & 0xFFFFFFFF))
 
     def uniform2(self, stream, index, sel=None):

@@ -176,6 +176,54 @@ int kb_reset(KbHandle* h, const uint8_t* mask, const double* body_pose, const do
              const double* kb_velocity, void* stream);
 
 /*
+ * Reset with on-device scene sampling.  The reference re-draws its scene in every reset():
+ * YamlKilobotsEnv._configure_environment (yaml_kilobots_env.py:194-198 objects, :256-283 lights, :299 shuffle of the
+ * composite light's components, :327-354 kilobots) with numpy's global generator, one env at a time.  Here the reset
+ * kernel draws the scene itself, as a pure function of (seed, global env id = env_id_base + env, episode count of the
+ * env) -- Philox4x32-10, one block per draw -- so an auto-reset is ONE launch, never touches the host, and 1 GPU and
+ * 8 GPUs reset an environment identically.  gym_kilobots_b200/sampler.py evaluates the same function in numpy.
+ *   objects[i].mode   KB_SAMPLE_FIXED (pose) | KB_SAMPLE_RANDOM ((U^2 * size + lo) * 0.7, U * 2 pi - pi)
+ *   lights[c].mode    per light component in the configuration's order: FIXED (init) | RANDOM (U^2 * size + lo) |
+ *                     AT_OBJECT (radius 1.2 * extent / 2 around a random object); momentum lights start with speed .01
+ *   shuffle_lights    composite light with init 'random': Fisher-Yates over the components.  Every permutation must be
+ *                     a scene template of the batch (light constants are per scene); perm_scene[rank] = its scene index,
+ *                     rank = lexicographic rank of (component at position 0, 1, ...).  The env's scene is switched.
+ *   kilobot_mean_mode KB_SAMPLE_FIXED (kilobot_mean) | KB_SAMPLE_MEAN_LIGHT | KB_SAMPLE_MEAN_RANDOM
+ */
+#define KB_SAMPLE_FIXED 0
+#define KB_SAMPLE_RANDOM 1
+#define KB_SAMPLE_AT_OBJECT 2
+#define KB_SAMPLE_MEAN_LIGHT 1
+#define KB_SAMPLE_MEAN_RANDOM 2
+typedef struct KbSampleObject {
+  int32_t mode, reserved;
+  double pose[3];      /* x m, y m, theta (KB_SAMPLE_FIXED) */
+  double extent;       /* max(width, height) of the object as Body.width / Body.height report it */
+} KbSampleObject;
+typedef struct KbSampleLight {
+  int32_t mode, reserved;
+  double init[2];      /* position (KB_SAMPLE_FIXED); init[0] = angle of a linear light */
+} KbSampleLight;
+typedef struct KbSampleSpec {
+  uint64_t seed;
+  int64_t env_id_base;             /* global id of this handle's env 0 (rank * envs per rank) */
+  double world_width, world_height;
+  int32_t num_objects, num_lights;
+  const KbSampleObject* objects;
+  const KbSampleLight* lights;
+  int32_t shuffle_lights, kilobot_mean_mode;
+  const int32_t* perm_scene;       /* [num_lights!] or NULL */
+  double kilobot_mean[2], kilobot_std;
+} KbSampleSpec;
+int kb_set_sampler(KbHandle* h, const KbSampleSpec* spec);          /* also restarts the episode counts */
+/* like kb_reset, with the poses / light states drawn on the device; mask: device u8[E] or NULL */
+int kb_reset_sampled(KbHandle* h, const uint8_t* mask, void* stream);
+/* what the last sampled resets drew: host f64[E,B,3], f64[E,L], i32[E] scene per env, u32[E] resets so far (any may be NULL) */
+int kb_get_sampled(KbHandle* h, double* body_pose, double* light_state, int32_t* env_scene, uint32_t* episodes);
+/* overwrite the env -> scene map (host i32[E]); takes effect at the env's next reset */
+int kb_set_env_scene(KbHandle* h, const int32_t* env_scene);
+
+/*
  * step (kilobots_env.py:161-215): steps_per_action sub-steps of
  *   light.step -> sensing -> controllers -> b2World.Step(dt, vel_iters, pos_iters)
  * then gathers the observation (get_state :115-118).  All pointers are device pointers.

@@ -125,6 +125,11 @@ class OracleBatch:
         m = None if body_mask is None else np.ascontiguousarray(body_mask, dtype=np.uint8).reshape(self.E, self.B)
         self.fn["set_poses_masked"](self.h, _ptr(pose), _ptr(m))
 
+    def set_env_scene(self, env_scene):
+        es = np.ascontiguousarray(env_scene, dtype=np.int32).reshape(self.E)
+        rc = self.fn["set_env_scene"](self.h, _ptr(es))
+        assert rc == 0
+
     def get_status(self):
         out = np.zeros(self.E, np.int32)
         self.fn["get_status"](self.h, _ptr(out))

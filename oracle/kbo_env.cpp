@@ -674,6 +674,17 @@ int kbo_set_poses_masked(KbHandle* hh, const double* pose, const uint8_t* body_m
 
 int kbo_set_poses(KbHandle* hh, const double* pose) { return kbo_set_poses_masked(hh, pose, nullptr); }
 
+// env -> scene map (takes effect at the env's next reset): mirrors kb_set_env_scene, so that tests can replay the
+// scene switches of the device-side sampler
+int kbo_set_env_scene(KbHandle* hh, const int32_t* env_scene) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  for (size_t i = 0; i < h->envs.size(); ++i) {
+    if (env_scene[i] < 0 || env_scene[i] >= (int)h->scenes.size()) return KB_ERR_INVALID;
+    h->envs[i].scene = env_scene[i];
+  }
+  return KB_OK;
+}
+
 int kbo_get_status(KbHandle* hh, int32_t* out) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   for (size_t i = 0; i < h->envs.size(); ++i) out[i] = h->envs[i].status;

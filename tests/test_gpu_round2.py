@@ -164,3 +164,27 @@ def test_episode_stats_reduction_matches_the_per_env_statistics(native):
     b = env.batch.reduce_episode_stats().cpu().numpy()
     assert np.array_equal(a, b)
     env.close()
+
+
+@pytest.mark.parametrize("chunks", ["1", "3", "8"])
+def test_pipelined_host_step_equals_the_device_step(native, chunks, monkeypatch):
+    """kb_step_host splits a large batch into chunks whose copies overlap the next chunk's kernel (two side streams);
+    the results must not depend on the chunking (ragged last chunk, ragged last block)."""
+    from gym_kilobots_b200.envs import KilobotsVecEnv
+    monkeypatch.setenv("KB_HOST_CHUNKS", chunks)
+    sc = SC.c5_small(1003)
+    a = KilobotsVecEnv(sc)
+    monkeypatch.setenv("KB_HOST_CHUNKS", "1")
+    b = KilobotsVecEnv(sc)
+    a.reset()
+    b.reset()
+    acts = SC.random_actions(sc, sc.num_envs, 6)
+    for t in range(6):
+        oa, ra, da, ia = a.step(acts[t])
+        ob_, rb, db, ib = b.step_device(acts[t])
+        for k in ("kilobots", "objects", "light"):
+            assert np.array_equal(oa[k], ob_[k].cpu().numpy()), (chunks, t, k)
+        assert np.array_equal(ra, rb.cpu().numpy()) and np.array_equal(ia["status"], ib["status"].cpu().numpy())
+    assert np.array_equal(a.batch.bodies(), b.batch.bodies())
+    a.close()
+    b.close()
