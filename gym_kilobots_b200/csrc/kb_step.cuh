@@ -234,10 +234,10 @@ struct Sim {
     const int n4 = L.stateWords >> 2;
 #pragma unroll 1
     for (int i = g.lane; i < n4; i += LPE) sts_f4(sa + 16u * (uint32_t)i, src[i]);
-    g.sync();
+    g.usync();
   }
   __device__ __forceinline__ void storeState() {
-    g.sync();
+    g.usync();
     float4* dst = reinterpret_cast<float4*>(blob);
     const int n4 = L.stateWords >> 2;
 #pragma unroll 1
@@ -288,7 +288,7 @@ struct Sim {
 #pragma unroll 1
     for (int w = g.lane; w < LC_WORDS * L.numLights; w += LPE)
       word(L.sLc + w) = __ldg(reinterpret_cast<const uint32_t*>(lights) + w);
-    g.sync();
+    g.usync();
     const int nC = (int)hdr(H_NC);
 #pragma unroll 1
     for (int i = g.lane; i < nC; i += LPE) {
@@ -297,7 +297,7 @@ struct Sim {
       adj(pa, pb >> 5).atomOr(1u << (pb & 31));
       adj(pb, pa >> 5).atomOr(1u << (pa & 31));
     }
-    g.sync();
+    g.usync();
   }
 
   // --------------------------------------------------------------------------- lights
@@ -358,7 +358,7 @@ struct Sim {
         }
       }
     }
-    g.sync();
+    g.usync();
   }
 
   __device__ __forceinline__ void lightValueGrad(const LCs lc, const SF64Arr ls, double sx, double sy,
@@ -433,7 +433,7 @@ struct Sim {
         }
       }
     }
-    g.sync();
+    g.usync();
   }
 
   __device__ __forceinline__ void senseControl() {
@@ -543,7 +543,7 @@ struct Sim {
         default: break;
       }
     }
-    g.sync();
+    g.usync();
   }
 
   // --------------------------------------------------------------------------- narrowphase
@@ -1420,10 +1420,11 @@ struct Sim {
       isl(b) = -1;
       lastLvl(b) = 0u;
     }
-    g.sync();
+    g.usync();
     int K = 0;
+    const int nCU = g.umax(nC);   // warp-uniform trip count: one full-mask vote serves every lane group of the warp
 #pragma unroll 1
-    for (int base = 0; base < nC; base += LPE) {
+    for (int base = 0; base < nCU; base += LPE) {
       const int i = nC - 1 - (base + g.lane);
       bool t = false;
       uint32_t val = 0u;
@@ -1442,7 +1443,7 @@ struct Sim {
           val = (uint32_t)i | ((uint32_t)bA << 16) | ((uint32_t)bB << 22) | (simple ? 0u : TL_GEN);
         }
       }
-      const uint32_t m = g.ballot(t);
+      const uint32_t m = g.uballot(t);
       const int dst = K + __popc(m & g.lt());
       if (t && dst < L.Kmax) {
         tl(dst) = val;
@@ -1461,7 +1462,7 @@ struct Sim {
 #pragma unroll 1
     for (int bb = 0; bb < B; bb += LPE) {
       const int b = bb + g.lane;
-      awakeMask |= (unsigned long long)g.ballot(b < B && awake(b)) << bb;
+      awakeMask |= (unsigned long long)g.uballot(b < B && awake(b)) << bb;
     }
     g.usync();
     // awake bodies without a touching contact are islands of their own (b2World::Solve seeds them like any other
@@ -1479,7 +1480,7 @@ struct Sim {
             const uint4 m = lds_u4(wa(L.sBmask + b * KW + w4));
             c |= (m.x | m.y | m.z | m.w) != 0u;
           }
-        hasC |= (unsigned long long)g.ballot(c) << bb;
+        hasC |= (unsigned long long)g.uballot(c) << bb;
       }
       lonely = awakeMask & ~hasC;
     }
@@ -1614,7 +1615,7 @@ struct Sim {
           pts += 1u;
         }
       }
-      nPts += g.red_add(pts);
+      nPts += g.ured_add(pts);
     }
     g.usync();
     KB_T(4);
@@ -1707,8 +1708,10 @@ struct Sim {
           }
           g.usync();
         }
-        const unsigned long long badAll = (unsigned long long)g.red_or((uint32_t)bad) |
-                                          ((unsigned long long)g.red_or((uint32_t)(bad >> 32)) << 32);
+        // (the sweep loop is warp-uniform; envs of one batch share B, so `nIslands >= 32` could only differ between
+        //  groups in its value, never in whether the second word exists)
+        unsigned long long badAll = (unsigned long long)g.ured_or((uint32_t)bad);
+        if (L.B > 32) badAll |= (unsigned long long)g.ured_or((uint32_t)(bad >> 32)) << 32;
         unsolved &= badAll;
       }
       // bit 1: positionSolved (sleep bookkeeping below adds bit 2: minSleepTime < timeToSleep)
@@ -1741,7 +1744,7 @@ struct Sim {
         if (!(st >= KB_TIME_TO_SLEEP)) islflag(island).atomOr(4u);  // minSleepTime < timeToSleep
       }
     }
-    g.sync();
+    g.usync();
     if (L.enableSleep) {
 #pragma unroll 1
       for (int b = g.lane; b < B; b += LPE) {
@@ -1754,7 +1757,7 @@ struct Sim {
           pos4(b).set(3, 0.0f);
         }
       }
-      g.sync();
+      g.usync();
     }
     g.usync();
     KB_T(8);
@@ -1833,13 +1836,14 @@ struct Sim {
         if (p < 32) mlo |= 1u << p; else mhi |= 1u << (p - 32);
       }
     }
-    mlo = g.red_or(mlo);
-    mhi = g.red_or(mhi);
+    // (from solve() this is warp-uniform control flow; the TOI caller is not)
+    mlo = toiMode ? g.red_or(mlo) : g.ured_or(mlo);
+    if (L.P > 32) mhi = toiMode ? g.red_or(mhi) : g.ured_or(mhi);
     if (g.lane == 0) {
       hdr(H_MOVED) |= mlo;
-      hdr(H_MOVED + 1) |= mhi;
+      if (L.P > 32) hdr(H_MOVED + 1) |= mhi;
     }
-    g.sync();
+    if (toiMode) g.sync(); else g.usync();
   }
 
   // b2BroadPhase::UpdatePairs + b2ContactManager::AddPair.  Pairs (i < j) with a moved member are
@@ -1981,7 +1985,7 @@ struct Sim {
 
   // get_state (kilobots_env.py:115-118) + the reward / done / info hooks (:123-131)
   __device__ __forceinline__ void gather(const KernelArgs& a, int env) {
-    g.sync();
+    g.sync();   // padding groups skip gather: not warp-uniform
     const int M = L.M, N = L.N;
     bool bad = false;
     float* flat = a.obsFlat ? a.obsFlat + (size_t)env * (2 * N + L.L + 4 * M) : nullptr;
@@ -2019,7 +2023,7 @@ struct Sim {
         if (flat) flat[2 * N + i] = (float)v;
       }
     }
-    g.sync();
+    g.sync();   // padding groups skip gather: not warp-uniform
     if (g.lane == 0) {
       float rew = __ldg(&a.scenes[a.envScene ? a.envScene[env] : 0].rewardConst);
       uint8_t dn = 0;
