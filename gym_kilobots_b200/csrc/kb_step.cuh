@@ -628,24 +628,29 @@ struct Sim {
 
   // b2ContactManager::Collide.  World-list order is descending array index; a sleeping pair is
   // only visited if an earlier (higher index) contact woke one of its bodies.
+  // Written in warp-uniform style: every lane group of the warp walks the same chunks and passes (the trip counts
+  // are the warp's maxima), groups that have nothing left to do run them empty, and the votes / barriers are the
+  // full-mask u-variants (outside uniform mode they are the group's own).
   __device__ __forceinline__ void collide() {
     const int nC = (int)hdr(H_NC);
-    if (nC == 0) return;
+    if (!g.uany(nC != 0)) return;
     // any sleeping dynamic body?
     bool sleepy = false;
 #pragma unroll 1
     for (int b = g.lane; b < L.B; b += LPE) sleepy |= !awake(b);
-    const bool anyAsleep = g.any(sleepy);
+    const uint32_t sleepyMask = g.uballot(sleepy);   // every lane votes (no short-circuit around a full-mask vote)
+    const bool anyAsleep = nC != 0 && sleepyMask != 0u;
+    const bool anyAsleepU = g.uany(anyAsleep);
     // stk(b) doubles as wakeAt[b]: per body, the highest contact index that woke it
     if (anyAsleep) {
 #pragma unroll 1
       for (int b = g.lane; b <= L.B; b += LPE) stk(b) = awake(b) ? 0x7FFFFFFF : -1;
-      g.sync();
     }
+    if (anyAsleepU) g.usync();
     bool anyDestroyed = false;
     // chunks from the top: a wake-up caused by a contact reaches every lower-index contact of later chunks in
     // the same pass; another pass is only needed after a pass that woke somebody
-    const int top = ((nC - 1) / LPE) * LPE;
+    const int top = g.umax((nC + LPE - 1) / LPE) * LPE - LPE;
     for (int pass = 0;; ++pass) {
       bool woke = false;
 #pragma unroll 1
@@ -654,7 +659,7 @@ struct Sim {
         bool doit = false;
         int pa = 0, pb = 0, bA = S, bB = S;
         uint32_t w = 0u;
-        if (i < nC) {
+        if (i < nC && (pass == 0 || anyAsleep)) {
           w = cw(i);
           if ((w & CI_DONE) == 0u) {
             pa = CW_PA(w);
@@ -691,24 +696,27 @@ struct Sim {
             woke = true;
           }
         }
-        if (anyAsleep) g.sync();
+        if (anyAsleepU) g.usync();
       }
-      if (!anyAsleep) break;
-      if (!g.any(woke)) break;
+      if (!anyAsleepU) break;
+      const uint32_t wokeMask = g.uballot(woke);
+      const bool again = wokeMask != 0u && anyAsleep;
+      if (!g.uany(again)) break;
     }
-    g.sync();
+    g.usync();
     if (anyAsleep) {
 #pragma unroll 1
       for (int b = g.lane; b < L.B; b += LPE)
         if ((int32_t)stk(b) >= 0) wake(b);
-      g.sync();
     }
+    if (anyAsleepU) g.usync();
     // clear DONE marks; stable compaction if anything was destroyed
-    const bool compact = g.any(anyDestroyed);
-    if (!compact && !anyAsleep) return;
+    const bool compact = g.uballot(anyDestroyed) != 0u;
+    if (!g.uany(compact || anyAsleep)) return;
     int out = 0;
+    const int nCU = g.umax(nC);
 #pragma unroll 1
-    for (int base = 0; base < nC; base += LPE) {
+    for (int base = 0; base < nCU; base += LPE) {
       const int i = base + g.lane;
       uint32_t w = 0u;
       bool keep = false;
@@ -717,19 +725,15 @@ struct Sim {
         keep = (w & CI_DESTROY) == 0u;
         w &= ~(CI_DONE | CI_DESTROY);
       }
-      if (!compact) {
-        if (i < nC) cw(i) = w;
-        continue;
-      }
-      const uint32_t m = g.ballot(keep);
-      const int dst = out + __popc(m & g.lt());
+      const uint32_t m = g.uballot(keep);
+      const int dst = compact ? out + __popc(m & g.lt()) : i;
       float4 r0, r1, r2, r3;
       const bool moveRec = keep && dst != i && (w & CI_PC_MASK) != 0u;
       if (moveRec) {
         const float4* rec = reinterpret_cast<const float4*>(manifoldRec(i));
         r0 = rec[0]; r1 = rec[1]; r2 = rec[2]; r3 = rec[3];
       }
-      g.sync();
+      g.usync();
       if (keep) {
         cw(dst) = w;
         if (moveRec) {
@@ -738,12 +742,12 @@ struct Sim {
         }
       }
       out += __popc(m);
-      g.sync();
+      g.usync();
     }
     if (compact) {
       if (g.lane == 0) hdr(H_NC) = (uint32_t)out;
     }
-    g.sync();
+    g.usync();
   }
 
   // ------------------------------------------------------------------------------ solver
@@ -1763,7 +1767,7 @@ struct Sim {
     KB_T(8);
     synchronizeFixtures(false);
     KB_T(9);
-    findNewContacts();
+    findNewContactsT<true>();   // u-variants degrade to the group's own outside uniform mode (reset kernel)
     g.usync();
     KB_T(10);
   }
@@ -1852,11 +1856,17 @@ struct Sim {
   // collects the new pairs in a 64-bit mask; an exclusive scan over the rows of a chunk gives every
   // row its place in the contact list.  Rows are independent: a new pair (i, j) never changes what a
   // later row has to test.
-  __device__ __forceinline__ void findNewContacts() {
+  // U: called from warp-uniform control flow (solve() in uniform mode): the loops run the warp's maximal trip counts,
+  // groups without work run them empty, and the votes / scans are the full-mask forms.  The TOI path and the reset
+  // kernel call the group form.
+  __device__ __forceinline__ void findNewContacts() { findNewContactsT<false>(); }
+  template <bool U>
+  __device__ __forceinline__ void findNewContactsT() {
     const uint32_t mlo = hdr(H_MOVED), mhi = hdr(H_MOVED + 1);
-    g.sync();
-    if ((mlo | mhi) == 0u) return;
-    if (g.lane == 0) {
+    if (U) g.usync(); else g.sync();
+    const bool some = (mlo | mhi) != 0u;
+    if (U ? !g.uany(some) : !some) return;
+    if (some && g.lane == 0) {
       hdr(H_MOVED) = 0u;
       hdr(H_MOVED + 1) = 0u;
     }
@@ -1868,7 +1878,8 @@ struct Sim {
     uint32_t tests = 0u;
 #pragma unroll 1
     for (int ib = 0; ib < P - 1; ib += LPE) {
-      if ((moved >> ib) == 0ull) break;  // neither a row from here on nor any of their columns moved
+      const bool more = (moved >> ib) != 0ull;   // a row from here on, or one of their columns, moved
+      if (U ? !g.uany(more) : !more) break;
       const int i = ib + g.lane;
       unsigned long long cand = 0ull;
       int bi = S;
@@ -1893,9 +1904,10 @@ struct Sim {
         }
       }
       const int cnt = __popcll(cand);
-      if (!g.any(cnt != 0)) continue;
-      const int off = g.exscan(cnt);
-      const int total = g.bcast(off + cnt, LPE - 1);
+      const uint32_t newMask = U ? g.uballot(cnt != 0) : g.ballot(cnt != 0);
+      if (U ? !g.uany(newMask != 0u) : newMask == 0u) continue;
+      const int off = U ? g.uexscan(cnt) : g.exscan(cnt);
+      const int total = U ? g.ubcast(off + cnt, LPE - 1) : g.bcast(off + cnt, LPE - 1);
       if (cnt != 0) {
         int dst = nC + off;
         const int ti = ptype(i);
@@ -1921,10 +1933,13 @@ struct Sim {
       }
       nC = min(nC + total, L.Cmax);
     }
-    nTests += g.red_add(tests);
-    if (g.lane == 0) hdr(H_NC) = (uint32_t)nC;
-    if (g.any(overflow) && g.lane == 0) hdr(H_STATUS) |= KB_STATUS_CONTACT_OVERFLOW;
-    g.sync();
+    nTests += U ? g.ured_add(tests) : g.red_add(tests);
+    const uint32_t ovMask = U ? g.uballot(overflow) : g.ballot(overflow);
+    if (some && g.lane == 0) {
+      hdr(H_NC) = (uint32_t)nC;
+      if (ovMask != 0u) hdr(H_STATUS) |= KB_STATUS_CONTACT_OVERFLOW;
+    }
+    if (U) g.usync(); else g.sync();
   }
 
   // b2World::Step(dt, velIters, posIters)
@@ -1942,7 +1957,8 @@ struct Sim {
       bool wallContact = false;
 #pragma unroll 1
       for (int i = g.lane; i < nC; i += LPE) wallContact |= pbody(CW_PA(cw(i))) == S;
-      if (g.any(wallContact)) nToi += solveTOINI(*this);
+      const uint32_t wallMask = g.uballot(wallContact);
+      if (wallMask != 0u) nToi += solveTOINI(*this);
       g.usync();
       KB_T(11);
     }
