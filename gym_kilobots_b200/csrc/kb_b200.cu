@@ -1000,9 +1000,9 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   }
 #undef KB_SET_SMEM
   {
-    // end-to-end pipeline depth: one chunk per ~8 MB of outputs, at most 8, each a whole number of blocks and at
+    // end-to-end pipeline depth: one chunk per ~2 MB of outputs, at most 8, each a whole number of blocks and at
     // least a few waves long (small batches -- C2's 4096 envs are ONE wave -- stay a single launch)
-    const int64_t chunkBytes = 8 << 20;
+    const int64_t chunkBytes = 2 << 20;
     int nc = (int)std::min<int64_t>(8, std::max<int64_t>(1, h->hostTotal / chunkBytes));
     const int blocks = launchGrid(h);
     while (nc > 1 && blocks / nc < 4 * 148) --nc;
@@ -1598,7 +1598,6 @@ int kb_render(KbHandle* hh, const int32_t* env_ids, int32_t num_images, int32_t 
   if (!h || !env_ids || !rgb || num_images < 1 || width < 1 || height < 1)
     return fail(KB_ERR_INVALID, "kb_render: invalid arguments");
   if (num_images > 65535) return fail(KB_ERR_INVALID, "kb_render: at most 65535 images per call");
-  if (h->W.enabled) return fail(KB_ERR_CAPACITY, "kb_render: not available for the large-swarm tier");
   for (int i = 0; i < num_images; ++i)
     if (env_ids[i] < 0 || env_ids[i] >= h->numEnvs) return fail(KB_ERR_INVALID, "kb_render: env id out of range");
   CUDA_TRY(cudaSetDevice(h->device));

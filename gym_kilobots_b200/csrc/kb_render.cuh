@@ -94,15 +94,19 @@ __global__ void __launch_bounds__(256) kb_render_kernel(const RenderArgs a) {
   const int env = a.envIds[img];
   const float* blob = a.blobs + (size_t)env * a.L.blobWords;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int b = tid; b < a.L.B; b += blockDim.x * blockDim.y)
-    xf[b] = *reinterpret_cast<const float4*>(blob + a.L.oXf + 4 * b);
+  // transforms staged in shared memory for the lane-group tier (<= 62 bodies); a large swarm is read through L2
+  const bool staged = a.L.B <= KB_MAX_BODIES;
+  if (staged)
+    for (int b = tid; b < a.L.B; b += blockDim.x * blockDim.y)
+      xf[b] = *reinterpret_cast<const float4*>(blob + a.L.oXf + 4 * b);
   __syncthreads();
+  const float4* xfp = staged ? xf : reinterpret_cast<const float4*>(blob + a.L.oXf);
   const int px_ = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
   if (px_ >= a.width || py >= a.height) return;
   const int scene = a.envScene ? a.envScene[env] : 0;
   const float x = a.x0 + ((float)px_ + 0.5f) * ((a.x1 - a.x0) / (float)a.width);
   const float y = a.y1 - ((float)py + 0.5f) * ((a.y1 - a.y0) / (float)a.height);   // image row 0 = top
-  const Rgb c = shadePixel(a, xf, reinterpret_cast<const double*>(blob + a.L.oLight), a.proxies + (size_t)scene * a.L.Pp,
+  const Rgb c = shadePixel(a, xfp, reinterpret_cast<const double*>(blob + a.L.oLight), a.proxies + (size_t)scene * a.L.Pp,
                            a.bodies + (size_t)scene * a.L.Bp, a.lights + (size_t)scene * (a.L.numLights > 0 ? a.L.numLights : 1),
                            a.scenes[scene].numProxies, a.scenes[scene].wallEdges, x, y);
   uint8_t* o = a.out + (((size_t)img * a.height + py) * a.width + px_) * 3;

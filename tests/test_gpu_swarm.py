@@ -120,3 +120,19 @@ def test_swarm_tier_scope_is_enforced(native):
                        num_objects=1, lights=[S.LightSpec(abi.KB_LIGHT_CIRCULAR, radius=.2)], world_size=(2.0, 1.5))
     with pytest.raises(RuntimeError, match="kilobots only"):
         native.NativeBatch([spec], 2)
+
+
+def test_swarm_render_matches_oracle(oracle, native):
+    """KilobotsEnv.render's picture (kilobots_env.py:221-275) of a 256-kilobot swarm, byte for byte vs the oracle's."""
+    sc = SC.c4_swarm(2, side=16)
+    ob = oracle.OracleBatch(sc.scenes, 2, sc.env_scene, sc.max_contacts)
+    nb = native.NativeBatch(sc.scenes, 2, sc.env_scene, sc.max_contacts)
+    ob.reset(sc.body_pose, sc.light_state)
+    nb.reset(sc.body_pose, sc.light_state)
+    for _ in range(2):
+        ob.step(np.zeros((2, 2)))
+        nb.step(np.zeros((2, 2)))
+    a = ob.render((0, 1), 400, 300)
+    b = nb.render((0, 1), 400, 300).cpu().numpy()
+    assert a.shape == b.shape == (2, 300, 400, 3) and np.array_equal(a, b)
+    assert (b == 150).all(axis=-1).sum() > 1000      # kilobot discs were drawn
