@@ -135,4 +135,4 @@ def test_swarm_render_matches_oracle(oracle, native):
     a = ob.render((0, 1), 400, 300)
     b = nb.render((0, 1), 400, 300).cpu().numpy()
     assert a.shape == b.shape == (2, 300, 400, 3) and np.array_equal(a, b)
-    assert (b == 150).all(axis=-1).sum() > 1000      # kilobot discs were drawn
+    assert len(np.unique(b.reshape(-1, 3), axis=0)) >= 5   # table, border, light blend, kilobot disc / ring / heading under it
