@@ -697,9 +697,14 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   if (swarm) {
     SwarmLayout& W = h->W;
     W.enabled = 1;
-    L.Cmax = round4(max_contacts > 0 ? max_contacts : std::min(P * (P - 1) / 2, 8 * B + 32));
-    if (L.Cmax > 65532) L.Cmax = 65532;                         // 16-bit contact indices in the schedule
-    L.Kmax = round4(std::min(L.Cmax, 3 * B + 32));
+    // capacities: the caller's, else 8B + 32 persistent pairs and 3B + 32 touching contacts (hexagonal packing) --
+    // shrunk step by step (never below 5B + 32 / 2B + 32) until the CTA's image fits the SM's shared memory
+    int cmaxTry = round4(max_contacts > 0 ? max_contacts : std::min(P * (P - 1) / 2, 8 * B + 32));
+    if (cmaxTry > 65532) cmaxTry = 65532;                       // 16-bit contact indices in the schedule
+    int kmaxTry = round4(std::min(cmaxTry, 3 * B + 32));
+    for (;;) {
+    L.Cmax = cmaxTry;
+    L.Kmax = kmaxTry;
     L.Gmax = 0;
     L.KW = 0;
     W.movedWords = round4((P + 31) / 32);
@@ -776,6 +781,12 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     W.gPcnt = q; q += 4 * L.Pp;
     scratch = std::max(scratch, q);
     W.smemBytes = al(W.zScr + scratch, 16);
+    if ((size_t)W.smemBytes <= (size_t)prop.sharedMemPerBlockOptin) break;
+    const int kFloor = round4(2 * B + 32), cFloor = round4(5 * B + 32);   // (floors on the rounded values: the loop ends)
+    if (kmaxTry > kFloor) kmaxTry = std::max(kFloor, round4(kmaxTry - B / 4 - 4));
+    else if (max_contacts <= 0 && cmaxTry > cFloor) cmaxTry = std::max(cFloor, round4(cmaxTry - B / 2 - 4));
+    else break;   // reported below: does not fit
+    }
     L.lanesPerEnv = KB_SWARM_THREADS;
     L.smemWords = W.smemBytes / 4;
   } else {
@@ -903,7 +914,8 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
   }
   if (h->smemBytes > (size_t)prop.sharedMemPerBlockOptin) {
     delete h;
-    return fail(KB_ERR_CAPACITY, "kb_create: per-env shared-memory image too large; lower max_contacts");
+    return fail(KB_ERR_CAPACITY, swarm ? "kb_create: this swarm does not fit one SM's shared memory (about 1700 kilobots per env at the minimal capacities)"
+                                       : "kb_create: per-env shared-memory image too large; lower max_contacts");
   }
 
   std::vector<ProxyConst> allProxies;

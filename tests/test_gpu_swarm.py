@@ -113,6 +113,25 @@ def test_swarm_masked_reset_set_pose_and_resume(oracle, native):
         assert_same_obs(ref[t - 6], nb.step(acts[t]), "swarm: resume, step %d" % t)
 
 
+def test_largest_swarms_fit_by_shrinking_the_capacities(oracle, native):
+    """1521 kilobots in one env: kb_create shrinks the contact / solver capacities until the CTA's image fits the SM
+    (never below 5B + 32 pairs / 2B + 32 touching contacts); 2025 do not fit and are refused."""
+    sc = SC.c4_swarm(1, side=39)
+    ob = oracle.OracleBatch(sc.scenes, 1, sc.env_scene, sc.max_contacts)
+    nb = native.NativeBatch(sc.scenes, 1, sc.env_scene, sc.max_contacts)
+    ob.reset(sc.body_pose, sc.light_state)
+    nb.reset(sc.body_pose, sc.light_state)
+    oo, on = ob.step(np.zeros((1, 2))), nb.step(np.zeros((1, 2)))
+    assert np.array_equal(oo["kilobots"], on["kilobots"]) and np.array_equal(ob.bodies(), nb.bodies())
+    (po, no), (pn, nn) = ob.contacts(), nb.contacts()
+    assert np.array_equal(no, nn) and np.array_equal(po[:, :no[0]], pn[:, :no[0]])     # capacities differ, lists do not
+    assert nb.N == 1521 and nb.C < ob.C and nb.launch_config()["smem_bytes_per_block"] <= 232448
+    assert not nb.get_status().any()
+    with pytest.raises(RuntimeError, match="does not fit"):
+        big = SC.c4_swarm(1, side=45)
+        native.NativeBatch(big.scenes, 1)
+
+
 def test_swarm_tier_scope_is_enforced(native):
     """Pushable objects are outside the tier: kb_create says so instead of mis-simulating."""
     from gym_kilobots_b200 import scene as S
