@@ -701,7 +701,8 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     // shrunk step by step (never below 5B + 32 / 2B + 32) until the CTA's image fits the SM's shared memory
     int cmaxTry = round4(max_contacts > 0 ? max_contacts : std::min(P * (P - 1) / 2, 8 * B + 32));
     if (cmaxTry > 65532) cmaxTry = 65532;                       // 16-bit contact indices in the schedule
-    int kmaxTry = round4(std::min(cmaxTry, 3 * B + 32));
+    // (an explicit max_contacts also sizes the solver: stacked spawns touch more than 3 neighbours per body)
+    int kmaxTry = round4(std::min(cmaxTry, max_contacts > 0 ? max_contacts : 3 * B + 32));
     for (;;) {
     L.Cmax = cmaxTry;
     L.Kmax = kmaxTry;

@@ -81,7 +81,7 @@ class KilobotsVecEnv:
         return {n: st[:, i] for i, n in enumerate(abi.EPISODE_STAT_NAMES)}
 
     @classmethod
-    def from_configuration(cls, configuration, num_envs, seed=0, env_id_base=0, device=0, **kwargs):
+    def from_configuration(cls, configuration, num_envs, seed=0, env_id_base=0, device=0, max_contacts=0, **kwargs):
         """E YamlKilobotsEnv(configuration=...) as ONE batch whose scenes are drawn on the device: objects, light(s)
         and kilobots are re-sampled inside the reset kernel (counter-based, keyed by seed / global env id / episode),
         like every reference reset() re-draws them (yaml_kilobots_env.py:194-198,256-283,299,327-354).
@@ -91,7 +91,7 @@ class KilobotsVecEnv:
         sampler = SceneSampler(configuration, seed=seed, env_id_base=env_id_base)
         specs = sampler.scene_specs()
         pose, light, scene = sampler.sample_numpy(np.arange(num_envs), 0)
-        sc = scenarios.Scenario("yaml", specs, scene.astype(np.int32), pose, light)
+        sc = scenarios.Scenario("yaml", specs, scene.astype(np.int32), pose, light, max_contacts=max_contacts)
         vec = cls(sc, device=device, **kwargs)
         vec.use_device_sampler(sampler)
         return vec

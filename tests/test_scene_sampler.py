@@ -165,3 +165,49 @@ def test_device_sampler_vs_numpy_and_oracle(oracle, native, composite):
     assert np.array_equal(ph, pose[E // 2:]) and np.array_equal(lh, light[E // 2:]) and np.array_equal(sh, scene[E // 2:])
     vec.close()
     half.close()
+
+
+@pytest.mark.gpu
+def test_device_sampler_on_the_swarm_tier(oracle, native):
+    """80 kilobots and no object select the large-swarm tier; its reset kernel draws the scene the same way."""
+    from gym_kilobots_b200.envs import KilobotsVecEnv
+    import torch
+    text = """
+!EvalEnv
+width: 1.0
+height: 0.8
+resolution: 600
+objects: []
+light: !LightConf {type: circular, init: random, radius: .3}
+kilobots: !KilobotsConf {num: 80, mean: [0.1, -0.05], std: 0.08}
+"""
+    # (mean 'light' with a light at the table's edge stacks dozens of kilobots on the clip line: more touching contacts
+    #  than the tier's 3B + 32 solver capacity -- flagged, and a different test)
+    conf = yaml.load(text, Loader=yaml.Loader)
+    E = 12
+    vec = KilobotsVecEnv.from_configuration(conf, E, seed=5, env_id_base=40)
+    assert vec.batch.launch_config()["block_threads"] == 512
+    ob = oracle.OracleBatch(vec.scenario.scenes, E, vec.scenario.env_scene, vec.scenario.max_contacts, threads=8)
+    vec.reset()
+    pose, light, scene, ep = vec.batch.get_sampled()
+    ref = vec.sampler.sample_numpy(np.arange(E), 0)
+    assert np.abs(pose - ref[0]).max() <= 1e-12 and np.abs(light - ref[1]).max() <= 1e-12 and np.all(ep == 1)
+    ob.reset(pose, light)
+    assert np.array_equal(vec.batch.bodies(), ob.bodies())
+    acts = SC.random_actions(vec.scenario, E, 4)
+    for t in range(2):
+        o1, o2 = vec.step(acts[t])[0], ob.step(acts[t])
+        assert np.array_equal(o1["kilobots"], o2["kilobots"]) and np.array_equal(o1["light"], o2["light"])
+    done = torch.zeros(E, dtype=torch.uint8, device="cuda")
+    done[1::3] = 1
+    vec.reset_done(done)
+    m = done.cpu().numpy().astype(bool)
+    pose2, light2, _, ep2 = vec.batch.get_sampled()
+    assert np.array_equal(ep2, 1 + m.astype(np.uint32)) and np.array_equal(pose2[~m], pose[~m])
+    ob.reset(pose2, light2, mask=m.astype(np.uint8))
+    for t in range(2, 4):
+        o1, o2 = vec.step(acts[t])[0], ob.step(acts[t])
+        assert np.array_equal(o1["kilobots"], o2["kilobots"])
+    assert np.array_equal(vec.batch.bodies(), ob.bodies())
+    assert not vec.check_status().any()
+    vec.close()
