@@ -203,3 +203,32 @@ def test_from_envs_vectorises_yaml_envs(oracle):
             assert np.allclose(o["kilobots"], out["kilobots"][e], atol=1e-7)   # float32 observation vs float64 pose
             assert np.allclose(o["objects"], out["objects"][e], atol=1e-7)
             assert np.array_equal(o["light"], out["light"][e])
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """Every struct of include/kb_b200.h as gcc lays it out (sizeof and the offset of every field) against the ctypes
+    mirror in gym_kilobots_b200/_abi.py: the boundary is plain C, a drifted field would corrupt scenes silently."""
+    import subprocess
+    from gym_kilobots_b200 import _abi as abi
+    structs = ["KbFixtureDef", "KbBodyDef", "KbLightDef", "KbSceneDesc", "KbDims", "KbTaskDef", "KbLaunchConfig",
+               "KbSampleObject", "KbSampleLight", "KbSampleSpec"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "kb_b200.h"', 'int main(void) {']
+    for s in structs:
+        cls = getattr(abi, s)
+        lines.append('printf("%s %%zu", sizeof(%s));' % (s, s))
+        for name, _ in cls._fields_:
+            lines.append('printf(" %%zu", offsetof(%s, %s));' % (s, name))
+        lines.append('printf("\\n");')
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    assert len(out) == len(structs)
+    for line in out:
+        parts = line.split()
+        cls = getattr(abi, parts[0])
+        assert int(parts[1]) == ctypes.sizeof(cls), parts[0]
+        for (name, _), off in zip(cls._fields_, parts[2:]):
+            assert int(off) == getattr(cls, name).offset, (parts[0], name)
