@@ -374,7 +374,8 @@ def measure(rig, workload, E, steps, warmup, cpu_envs, steady_steps=0, sampler=N
                          "frac": flops_env * E / launch_s / 1e12 / fp32_peak,
                          "note": "non-tensor FP32 issue roofline (SURVEY 8d); no dense contraction on this path"}}
         cpu_n = min(E, cpu_envs)
-        cpu_val, cpu_sec, _ = time_oracle(workload, cpu_n, max(2, min(steps, 5)), 1, 1)
+        cpu_steps = max(2, steps)
+        cpu_val, cpu_sec, _ = time_oracle(workload, cpu_n, cpu_steps, 1, 1)
         out = {
             "workload": workload, "value": env_steps_s * N, "unit": UNIT, "ms_per_step": float(step_ms.mean()),
             "scaling": "strong" if workload in TOTAL_FIXED else "weak",
@@ -392,8 +393,8 @@ def measure(rig, workload, E, steps, warmup, cpu_envs, steady_steps=0, sampler=N
             "gpu_launches": int(steps),
             "roofline": roof,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": "%d envs of the workload, oracle/libkbo.so single thread (Box2D restatement; "
-                                       "pybox2d not installable offline)" % cpu_n},
+                             "sample": "%d envs of the workload x %d env-steps (%.1f s), oracle/libkbo.so single thread (Box2D "
+                                       "restatement; pybox2d not installable offline)" % (cpu_n, cpu_steps, cpu_sec * cpu_steps)},
             "episode_stats_all_reduced": job_stats,
             "sim_stats": {"contacts_per_substep": C_mean, "manifold_points_per_substep": pts,
                           "gs_levels_per_substep": lvls, "islands_per_substep": isl,
@@ -425,7 +426,7 @@ def run_ours(args):
             if wl == args.workload:
                 continue
             r = measure(rig, wl, envs_per_gpu(wl, world), max(5, args.steps // 2), max(3, args.warmup // 2),
-                        min(args.cpu_envs, 16 if wl == "c4" else 64))
+                        min(args.cpu_envs, {"c4": 8, "c3": 128, "c5": 4096}.get(wl, 256)))
             if r is not None:
                 sweep.append(r)
     if rig.rank == 0:
@@ -448,8 +449,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(DEFAULT_ENVS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
-    ap.add_argument("--cpu-envs", type=int, default=256, help="sample size of the cpu_baseline leg")
-    ap.add_argument("--ref-envs", type=int, default=2048, help="sample size of --impl reference")
+    ap.add_argument("--cpu-envs", type=int, default=2048, help="sample size of the cpu_baseline leg (envs, one thread)")
+    ap.add_argument("--ref-envs", type=int, default=4096, help="sample size of --impl reference (envs, all host cores)")
     ap.add_argument("--steady-steps", type=int, default=200,
                     help="env-steps of the steady-state leg with staggered auto-resets (0 = skip)")
     ap.add_argument("--sweep", default="c5,c3,c4",
