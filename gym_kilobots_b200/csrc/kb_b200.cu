@@ -788,7 +788,15 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     else if (max_contacts <= 0 && cmaxTry > cFloor) cmaxTry = std::max(cFloor, round4(cmaxTry - B / 2 - 4));
     else break;   // reported below: does not fit
     }
-    L.lanesPerEnv = KB_SWARM_THREADS;
+    {
+      // threads per CTA: as many CTAs per SM as shared memory holds, each as wide as the register file then allows
+      const int perSm = std::max(1, (int)((size_t)prop.sharedMemPerMultiprocessor / ((size_t)W.smemBytes + 1024)));
+      L.lanesPerEnv = perSm >= 4 ? 128 : (perSm >= 2 ? 256 : 512);
+      if (const char* ev = getenv("KB_SWARM_THREADS")) {
+        const int v = atoi(ev);
+        if (v == 128 || v == 256 || v == 512) L.lanesPerEnv = v;
+      }
+    }
     L.smemWords = W.smemBytes / 4;
   } else {
   // max_contacts > 0: the caller's capacity; 0: the throughput default (8B + 32 persistent pairs, 3B + 9 touching
@@ -1002,9 +1010,12 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     CUDA_TRY(cudaFuncSetAttribute(kb_setpose_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes)); \
     break;
   if (swarm) {
-    CUDA_TRY(cudaFuncSetAttribute(kb_swarm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(kb_swarm_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(kb_swarm_setpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+#define KB_SET_SWARM_SMEM(T)                                                                                           \
+    CUDA_TRY(cudaFuncSetAttribute(kb_swarm_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));  \
+    CUDA_TRY(cudaFuncSetAttribute(kb_swarm_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes)); \
+    CUDA_TRY(cudaFuncSetAttribute(kb_swarm_setpose_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    if (L.lanesPerEnv == 128) { KB_SET_SWARM_SMEM(128) } else if (L.lanesPerEnv == 256) { KB_SET_SWARM_SMEM(256) } else { KB_SET_SWARM_SMEM(512) }
+#undef KB_SET_SWARM_SMEM
   } else switch (L.lanesPerEnv) {
     KB_SET_SMEM(4)
     KB_SET_SMEM(8)
@@ -1067,7 +1078,11 @@ int kb_get_dims(const KbHandle* hh, KbDims* d) {
 // launches `kernel` over the envs [a.envOffset, a.envOffset + count)
 #define KB_LAUNCH_RANGE(kernel, swarmKernel, h, st, a, count)                                     \
   if ((h)->W.enabled) {                                                                           \
-    swarmKernel<<<(count), KB_SWARM_THREADS, (h)->smemBytes, (st)>>>(a);                              \
+    switch ((h)->L.lanesPerEnv) {                                                                 \
+      case 128: swarmKernel<128><<<(count), 128, (h)->smemBytes, (st)>>>(a); break;                     \
+      case 256: swarmKernel<256><<<(count), 256, (h)->smemBytes, (st)>>>(a); break;                     \
+      default: swarmKernel<512><<<(count), 512, (h)->smemBytes, (st)>>>(a); break;                      \
+    }                                                                                             \
   } else {                                                                                        \
     const int grid_ = ((count) + (h)->envsPerBlock - 1) / (h)->envsPerBlock;                      \
     switch ((h)->L.lanesPerEnv) {                                                                 \
@@ -1524,7 +1539,7 @@ int kb_get_launch_config(const KbHandle* hh, KbLaunchConfig* cfg) {
   const Handle* h = reinterpret_cast<const Handle*>(hh);
   if (!h || !cfg) return fail(KB_ERR_INVALID, "kb_get_launch_config: null");
   cfg->lanes_per_env = h->L.lanesPerEnv;
-  cfg->block_threads = h->W.enabled ? KB_SWARM_THREADS : KB_BLOCK_OF(h->L.lanesPerEnv);
+  cfg->block_threads = h->W.enabled ? h->L.lanesPerEnv : KB_BLOCK_OF(h->L.lanesPerEnv);
   cfg->grid_blocks = launchGrid(h);
   cfg->smem_bytes_per_block = (int32_t)h->smemBytes;
   cfg->state_words_per_env = h->L.stateWords;

@@ -30,7 +30,10 @@
 
 namespace kb {
 
-#define KB_SWARM_THREADS 512
+// threads per CTA: 512, 256 or 128 -- the widest block that still lets as many CTAs share an SM as its shared memory holds
+// (124 registers per thread: 512 threads x 1 CTA, 256 x 2, 128 x 4).  A second CTA on the SM overlaps perfectly with the
+// first (the solver keeps ONE warp busy): 296 envs of 484 kilobots take as long as 148.
+#define KB_SWARM_THREADS_MAX 512
 #define KB_SWARM_MAX_BODIES 2040   /* 11-bit proxy ids (bodies + table edges < 2048) */
 
 // swarm manifold record (8 words per contact, HBM/L2)
@@ -59,6 +62,7 @@ namespace kb {
 #define SW_T(i) do { } while (0)
 #endif
 
+template <int NT>
 struct Swarm {
   const Layout& L;
   const SwarmLayout& W;
@@ -143,7 +147,7 @@ struct Swarm {
     __syncthreads();   // previous users of the warp-sum words are done
     if (lane == 31) misc(16 + wid) = (uint32_t)x;
     __syncthreads();
-    const int nw = KB_SWARM_THREADS / 32;
+    const int nw = NT / 32;
     int ws = lane < nw ? (int)misc(16 + lane) : 0;
     int wx = ws;
 #pragma unroll
@@ -162,7 +166,7 @@ struct Swarm {
     const float4* bv = reinterpret_cast<const float4*>(blob + L.oVel);
     const float4* bx = reinterpret_cast<const float4*>(blob + L.oXf);
 #pragma unroll 1
-    for (int b = tid; b <= L.B; b += KB_SWARM_THREADS) {
+    for (int b = tid; b <= L.B; b += NT) {
       if (b < L.B) {
         pos4(b) = bp[b];
         vel4(b) = bv[b];
@@ -177,13 +181,13 @@ struct Swarm {
       }
     }
     const uint32_t* bw = reinterpret_cast<const uint32_t*>(blob);
-    for (int i = tid; i < H_WORDS; i += KB_SWARM_THREADS) hdr(i) = bw[L.oHdr + i];
-    for (int i = tid; i < W.movedWords; i += KB_SWARM_THREADS) moved(i) = bw[W.oMoved + i];
-    for (int i = tid; i < 2 * L.L; i += KB_SWARM_THREADS) sts_u32(sa + W.zLight + 4u * (uint32_t)i, bw[L.oLight + i]);
+    for (int i = tid; i < H_WORDS; i += NT) hdr(i) = bw[L.oHdr + i];
+    for (int i = tid; i < W.movedWords; i += NT) moved(i) = bw[W.oMoved + i];
+    for (int i = tid; i < 2 * L.L; i += NT) sts_u32(sa + W.zLight + 4u * (uint32_t)i, bw[L.oLight + i]);
     __syncthreads();
   }
   __device__ __forceinline__ void loadConsts(const LightConst* lights) {
-    for (int w = tid; w < LC_WORDS * L.numLights; w += KB_SWARM_THREADS)
+    for (int w = tid; w < LC_WORDS * L.numLights; w += NT)
       sts_u32(sa + W.zLc + 4u * (uint32_t)w, __ldg(reinterpret_cast<const uint32_t*>(lights) + w));
     __syncthreads();
   }
@@ -193,7 +197,7 @@ struct Swarm {
     float4* bv = reinterpret_cast<float4*>(blob + L.oVel);
     float4* bx = reinterpret_cast<float4*>(blob + L.oXf);
 #pragma unroll 1
-    for (int b = tid; b < L.B; b += KB_SWARM_THREADS) {
+    for (int b = tid; b < L.B; b += NT) {
       const float4 p = pos4(b);
       const float2 q = q2(b);
       bp[b] = p;
@@ -201,9 +205,9 @@ struct Swarm {
       bx[b] = make_float4(p.x, p.y, q.x, q.y);
     }
     uint32_t* bw = reinterpret_cast<uint32_t*>(blob);
-    for (int i = tid; i < H_WORDS; i += KB_SWARM_THREADS) bw[L.oHdr + i] = hdr(i);
-    for (int i = tid; i < W.movedWords; i += KB_SWARM_THREADS) bw[W.oMoved + i] = moved(i);
-    for (int i = tid; i < 2 * L.L; i += KB_SWARM_THREADS) bw[L.oLight + i] = lds_u32(sa + W.zLight + 4u * (uint32_t)i);
+    for (int i = tid; i < H_WORDS; i += NT) bw[L.oHdr + i] = hdr(i);
+    for (int i = tid; i < W.movedWords; i += NT) bw[W.oMoved + i] = moved(i);
+    for (int i = tid; i < 2 * L.L; i += NT) bw[L.oLight + i] = lds_u32(sa + W.zLight + 4u * (uint32_t)i);
     if (tid == 0) {
       unsigned long long* c = reinterpret_cast<unsigned long long*>(blob + L.oCnt);
       c[KB_CNT_SUBSTEPS] += nSub;
@@ -325,7 +329,7 @@ struct Swarm {
     const double hpi = 0.5 * 3.141592653589793;
     const double pi = 3.141592653589793;
 #pragma unroll 1
-    for (int k = tid; k < L.N; k += KB_SWARM_THREADS) {
+    for (int k = tid; k < L.N; k += NT) {
       const int kind = __ldg(&bc[k].kind);
       double* c = ctrl(k);
       const double* a = action ? action + 2 * k : nullptr;
@@ -342,7 +346,7 @@ struct Swarm {
   __device__ __forceinline__ void senseControl() {
     const SF64Arr ls = lightState();
 #pragma unroll 1
-    for (int k = tid; k < L.N; k += KB_SWARM_THREADS) {
+    for (int k = tid; k < L.N; k += NT) {
       const int b = k;   // M == 0
       const int kind = __ldg(&bc[b].kind);
       const Xf xf = bodyXf(b);
@@ -491,19 +495,19 @@ struct Swarm {
     if (nC == 0) return;
     bool sleepy = false;
 #pragma unroll 1
-    for (int b = tid; b < L.B; b += KB_SWARM_THREADS) sleepy |= !awake(b);
+    for (int b = tid; b < L.B; b += NT) sleepy |= !awake(b);
     const bool anyAsleep = __syncthreads_or(sleepy) != 0;
     const uint32_t wakeAt = scr(W.cWakeAt);
     if (anyAsleep) {
 #pragma unroll 1
-      for (int b = tid; b <= L.B; b += KB_SWARM_THREADS) sts_u32(wakeAt + 4u * (uint32_t)b, awake(b) && b != S ? 0x7FFFFFFFu : 0xFFFFFFFFu);
+      for (int b = tid; b <= L.B; b += NT) sts_u32(wakeAt + 4u * (uint32_t)b, awake(b) && b != S ? 0x7FFFFFFFu : 0xFFFFFFFFu);
       __syncthreads();
     }
     bool anyDestroyed = false;
     for (int pass = 0;; ++pass) {
       bool woke = false;
 #pragma unroll 1
-      for (int i = tid; i < nC; i += KB_SWARM_THREADS) {
+      for (int i = tid; i < nC; i += NT) {
         uint32_t w = cwp()[i];
         if ((w & CI_DONE) != 0u) continue;
         const uint32_t pr = cpairp()[i];
@@ -537,7 +541,7 @@ struct Swarm {
     __syncthreads();
     if (anyAsleep) {
 #pragma unroll 1
-      for (int b = tid; b < L.B; b += KB_SWARM_THREADS)
+      for (int b = tid; b < L.B; b += NT)
         if ((int32_t)lds_u32(wakeAt + 4u * (uint32_t)b) >= 0) wake(b);
     }
     const bool compact = __syncthreads_or(anyDestroyed) != 0;
@@ -546,7 +550,7 @@ struct Swarm {
     // a chunk only writes at or below its own first index)
     int out = 0;
 #pragma unroll 1
-    for (int base = 0; base < nC; base += KB_SWARM_THREADS) {
+    for (int base = 0; base < nC; base += NT) {
       const int i = base + tid;
       uint32_t w = 0u, pr = 0u;
       bool keep = false;
@@ -776,7 +780,7 @@ struct Swarm {
     const uint32_t lastLvl = scr(W.sLastLvl), cflag = scr(W.sCflag), lvlCnt = scr(W.sLvlCnt);
     // ---- touching list in world-list order (descending contact index)
 #pragma unroll 1
-    for (int b = tid; b <= B + 1; b += KB_SWARM_THREADS) {
+    for (int b = tid; b <= B + 1; b += NT) {
       sts_u16(bstart + 2u * (uint32_t)b, 0u);
       if (b <= B) {
         sts_u16(lastLvl + 2u * (uint32_t)b, 0u);
@@ -786,7 +790,7 @@ struct Swarm {
     __syncthreads();
     int K = 0;
 #pragma unroll 1
-    for (int base = 0; base < nC; base += KB_SWARM_THREADS) {
+    for (int base = 0; base < nC; base += NT) {
       const int i = nC - 1 - (base + tid);
       bool t = false;
       uint32_t bodies = 0u;
@@ -815,7 +819,7 @@ struct Swarm {
     // ---- per-body lists over the touching list (CSR), each sorted ascending == Box2D's contact-edge list order
     // degree counts: bstart[b + 1] (u16) by shared-memory atomics on the containing 32-bit word
 #pragma unroll 1
-    for (int t = tid; t < K; t += KB_SWARM_THREADS) {
+    for (int t = tid; t < K; t += NT) {
       const uint32_t bb = lds_u32(tlB + 4u * (uint32_t)t);
       const int bA = (int)(bb & 0xFFFFu), bB = (int)(bb >> 16);
       if (bA != S) atomicAddU16(bstart, bA + 1);
@@ -823,13 +827,13 @@ struct Swarm {
       sts_u8(cflag + (uint32_t)t, 0u);
     }
 #pragma unroll 1
-    for (int l = tid; l <= K + 1; l += KB_SWARM_THREADS) sts_u16(lvlCnt + 2u * (uint32_t)l, 0u);
+    for (int l = tid; l <= K + 1; l += NT) sts_u16(lvlCnt + 2u * (uint32_t)l, 0u);
     __syncthreads();
     {
       // exclusive scan of the degrees over the bodies (chunks of the CTA's width)
       int run = 0;
 #pragma unroll 1
-      for (int base = 0; base <= B; base += KB_SWARM_THREADS) {
+      for (int base = 0; base <= B; base += NT) {
         const int b = base + tid;
         const int deg = b <= B ? (int)lds_u16(bstart + 2u * (uint32_t)(b + 1)) : 0;
         int total;
@@ -845,7 +849,7 @@ struct Swarm {
       __syncthreads();
     }
 #pragma unroll 1
-    for (int t = tid; t < K; t += KB_SWARM_THREADS) {
+    for (int t = tid; t < K; t += NT) {
       const uint32_t bb = lds_u32(tlB + 4u * (uint32_t)t);
       const int bA = (int)(bb & 0xFFFFu), bB = (int)(bb >> 16);
       // entry = touching-list index | other body << 16
@@ -855,7 +859,7 @@ struct Swarm {
     __syncthreads();
     uint32_t lonelyCount = 0u;
 #pragma unroll 1
-    for (int b = tid; b < B; b += KB_SWARM_THREADS) {
+    for (int b = tid; b < B; b += NT) {
       const int s0 = (int)lds_u16(bstart + 2u * (uint32_t)b), s1 = (int)lds_u16(bstart + 2u * (uint32_t)(b + 1));
       for (int i = s0 + 1; i < s1; ++i) {   // insertion sort by list index (degree <= ~8)
         const uint32_t v = lds_u32(adj + 4u * (uint32_t)i);
@@ -933,12 +937,12 @@ struct Swarm {
     nLvl += (uint32_t)maxL;
     // ---- rows: rowStart[l] = first schedule entry of level l (exclusive scan of the level counts), then scatter
 #pragma unroll 1
-    for (int p = tid; p < nOrd; p += KB_SWARM_THREADS) atomicAddU16(lvlCnt, (int)lds_u16(ordL + 2u * (uint32_t)p));
+    for (int p = tid; p < nOrd; p += NT) atomicAddU16(lvlCnt, (int)lds_u16(ordL + 2u * (uint32_t)p));
     __syncthreads();
     {
       int run = 0;
 #pragma unroll 1
-      for (int base = 1; base <= maxL + 1; base += KB_SWARM_THREADS) {
+      for (int base = 1; base <= maxL + 1; base += NT) {
         const int l = base + tid;
         const int c = l <= maxL ? (int)lds_u16(lvlCnt + 2u * (uint32_t)l) : 0;
         int total;
@@ -954,7 +958,7 @@ struct Swarm {
     }
     // entries of one level touch disjoint dynamic bodies: their order within the level cannot influence any result
 #pragma unroll 1
-    for (int p = tid; p < nOrd; p += KB_SWARM_THREADS) {
+    for (int p = tid; p < nOrd; p += NT) {
       const int t = (int)lds_u16(ordT + 2u * (uint32_t)p);
       const int l = (int)lds_u16(ordL + 2u * (uint32_t)p);
       const uint32_t e = atomicAddU16(lvlCnt, l);
@@ -963,12 +967,12 @@ struct Swarm {
       entI((int)e) = lds_u16(ordI + 2u * (uint32_t)p);
     }
 #pragma unroll 1
-    for (int i = tid; i < nIslDfs; i += KB_SWARM_THREADS) sts_u8(islStateAddr(i), 1u);   // bit 0: unsolved
+    for (int i = tid; i < nIslDfs; i += NT) sts_u8(islStateAddr(i), 1u);   // bit 0: unsolved
     __syncthreads();
     // ---- b2Island::Solve: integrate velocities (damping), remember the sweep start
     const float h = L.dt;
 #pragma unroll 1
-    for (int b = tid; b < B; b += KB_SWARM_THREADS) {
+    for (int b = tid; b < B; b += NT) {
       if ((uint32_t)isl(b) == SW_NOISLAND) continue;
       const float4 p = pos4(b);
       sweepp()[b] = make_float4(p.x, p.y, p.z, 0.0f);
@@ -983,7 +987,7 @@ struct Swarm {
     }
     __syncthreads();   // the schedule is complete: the scratch lists are dead, the record region is free
 #pragma unroll 1
-    for (int e = tid; e < nOrd; e += KB_SWARM_THREADS) initSimple(e);
+    for (int e = tid; e < nOrd; e += NT) initSimple(e);
     nPts += (uint32_t)nOrd;
     __syncthreads();
     SW_T(5);
@@ -1011,10 +1015,10 @@ struct Swarm {
     __syncthreads();
     SW_T(6);
 #pragma unroll 1
-    for (int e = tid; e < nOrd; e += KB_SWARM_THREADS) storeSimple(e);
+    for (int e = tid; e < nOrd; e += NT) storeSimple(e);
     // ---- integrate positions
 #pragma unroll 1
-    for (int b = tid; b < B; b += KB_SWARM_THREADS) {
+    for (int b = tid; b < B; b += NT) {
       if ((uint32_t)isl(b) == SW_NOISLAND) continue;
       float4 p = pos4(b);
       float4 v = vel4(b);
@@ -1060,7 +1064,7 @@ struct Swarm {
       __syncthreads();
       uint32_t still = 0u;
 #pragma unroll 1
-      for (int i = tid; i < nIslDfs; i += KB_SWARM_THREADS) {
+      for (int i = tid; i < nIslDfs; i += NT) {
         const uint32_t st = lds_u8(islStateAddr(i));
         const uint32_t ns = (st & 2u) != 0u ? 1u : 0u;   // unsolved &= bad
         sts_u8(islStateAddr(i), ns);
@@ -1077,7 +1081,7 @@ struct Swarm {
     SW_T(8);
     // ---- copy back: SynchronizeTransform; sleep bookkeeping
 #pragma unroll 1
-    for (int b = tid; b < B; b += KB_SWARM_THREADS) {
+    for (int b = tid; b < B; b += NT) {
       const uint32_t island = isl(b);
       if (island == SW_NOISLAND) continue;
       const float4 p = pos4(b);
@@ -1100,7 +1104,7 @@ struct Swarm {
     __syncthreads();
     if (L.enableSleep) {
 #pragma unroll 1
-      for (int b = tid; b < B; b += KB_SWARM_THREADS) {
+      for (int b = tid; b < B; b += NT) {
         const uint32_t island = isl(b);
         if (island == SW_NOISLAND) continue;
         bool sleepNow;
@@ -1139,7 +1143,7 @@ struct Swarm {
   // A kilobot's proxy is a circle at the body origin with zero local centre: aabb(xf) = xf.p -+ r, xf1.p = c0.
   __device__ __forceinline__ void synchronizeFixtures(int only) {
 #pragma unroll 1
-    for (int b = tid; b < L.B; b += KB_SWARM_THREADS) {
+    for (int b = tid; b < L.B; b += NT) {
       if (only >= 0 ? b != only : (uint32_t)isl(b) == SW_NOISLAND) continue;
       const int p = nWall + b;
       const float4 sw = sweepp()[b];
@@ -1194,18 +1198,18 @@ struct Swarm {
   __device__ __forceinline__ void findNewContacts() {
     const int P = L.P;
     bool any = false;
-    for (int w = tid; w < W.movedWords; w += KB_SWARM_THREADS) any |= (uint32_t)moved(w) != 0u;
+    for (int w = tid; w < W.movedWords; w += NT) any |= (uint32_t)moved(w) != 0u;
     if (__syncthreads_or(any) == 0) return;
     int nC = (int)hdr(H_NC);
     const uint32_t table = scr(W.gHash), cellStart = scr(W.gCellStart), cellCur = scr(W.gCellCur), sorted = scr(W.gSorted);
     const uint32_t pcnt = scr(W.gPcnt);
     const int ncell = W.gx * W.gy;
     // ---- hash of the existing pairs; cell counts
-    for (int i = tid; i < W.hashSize; i += KB_SWARM_THREADS) sts_u32(table + 4u * (uint32_t)i, 0u);
-    for (int c = tid; c <= ncell; c += KB_SWARM_THREADS) sts_u32(cellStart + 4u * (uint32_t)c, 0u);
+    for (int i = tid; i < W.hashSize; i += NT) sts_u32(table + 4u * (uint32_t)i, 0u);
+    for (int c = tid; c <= ncell; c += NT) sts_u32(cellStart + 4u * (uint32_t)c, 0u);
     __syncthreads();
 #pragma unroll 1
-    for (int i = tid; i < nC; i += KB_SWARM_THREADS) {
+    for (int i = tid; i < nC; i += NT) {
       const uint32_t pr = cpairp()[i];
       const uint32_t pa = pr & 0xFFFFu, pb = pr >> 16;
       const uint32_t key = ((pa < pb ? pa : pb) << 16 | (pa < pb ? pb : pa)) + 1u;
@@ -1222,7 +1226,7 @@ struct Swarm {
     // adds the group size with one shared-memory atomic, every lane's slot is base + its rank in the group mask.
     float wmax = 0.0f;
 #pragma unroll 1
-    for (int base = nWall; base < P; base += KB_SWARM_THREADS) {
+    for (int base = nWall; base < P; base += NT) {
       const int p = base + tid;
       const bool valid = p < P;
       int cell = -1;
@@ -1252,7 +1256,7 @@ struct Swarm {
     {
       int run = 0;
 #pragma unroll 1
-      for (int base = 0; base < ncell; base += KB_SWARM_THREADS) {
+      for (int base = 0; base < ncell; base += NT) {
         const int c = base + tid;
         const int n = c < ncell ? (int)lds_u32(cellStart + 4u * (uint32_t)(c + 1)) : 0;
         int total;
@@ -1263,7 +1267,7 @@ struct Swarm {
       }
       __syncthreads();
     }
-    for (int p = nWall + tid; p < P; p += KB_SWARM_THREADS) {
+    for (int p = nWall + tid; p < P; p += NT) {
       const uint32_t cs = lds_u32(pcnt + 4u * (uint32_t)p);
       sts_u16(sorted + 2u * (lds_u32(cellStart + 4u * (cs >> 12)) + (cs & 0xFFFu)), (uint32_t)p);
     }
@@ -1276,7 +1280,7 @@ struct Swarm {
       const float4 fi = fatp()[i];
       const bool movedI = isMoved(i);
 #pragma unroll 1
-      for (int base = nWall; base < P; base += KB_SWARM_THREADS) {
+      for (int base = nWall; base < P; base += NT) {
         const int j = base + tid;
         bool c = false;
         if (j < P && (movedI || isMoved(j))) {
@@ -1300,7 +1304,7 @@ struct Swarm {
     }
     // ---- dynamic against dynamic through the grid: proxy i owns its pairs (i, j > i)
 #pragma unroll 1
-    for (int base = nWall; base < P; base += KB_SWARM_THREADS) {
+    for (int base = nWall; base < P; base += NT) {
       const int i = base + tid;
       int cnt = 0;
       float4 fi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1364,7 +1368,7 @@ struct Swarm {
       hdr(H_NC) = (uint32_t)nC;
       if (ov) hdr(H_STATUS) |= KB_STATUS_CONTACT_OVERFLOW;
     }
-    for (int w = tid; w < W.movedWords; w += KB_SWARM_THREADS) moved(w) = 0u;
+    for (int w = tid; w < W.movedWords; w += NT) moved(w) = 0u;
     __syncthreads();
   }
   __device__ __forceinline__ float blockMaxF(float v) const {
@@ -1374,7 +1378,7 @@ struct Swarm {
     if ((tid & 31) == 0) misc(16 + (tid >> 5)) = f2u(v);
     __syncthreads();
     float r = 0.0f;
-    for (int w = 0; w < KB_SWARM_THREADS / 32; ++w) r = b2max(r, u2f(misc(16 + w)));
+    for (int w = 0; w < NT / 32; ++w) r = b2max(r, u2f(misc(16 + w)));
     return r;
   }
 
@@ -1386,12 +1390,12 @@ struct Swarm {
     int nC = (int)hdr(H_NC);
     bool wall = false;
 #pragma unroll 1
-    for (int i = tid; i < nC; i += KB_SWARM_THREADS) wall |= (int)(cpairp()[i] & 0xFFFFu) < nWall;
+    for (int i = tid; i < nC; i += NT) wall |= (int)(cpairp()[i] & 0xFFFFu) < nWall;
     if (__syncthreads_or(wall) == 0) return;
 #pragma unroll 1
-    for (int b = tid; b < B; b += KB_SWARM_THREADS) reinterpret_cast<float*>(sweepp() + b)[3] = 0.0f;   // alpha0 = 0
+    for (int b = tid; b < B; b += NT) reinterpret_cast<float*>(sweepp() + b)[3] = 0.0f;   // alpha0 = 0
 #pragma unroll 1
-    for (int i = tid; i < nC; i += KB_SWARM_THREADS) {
+    for (int i = tid; i < nC; i += NT) {
       cwp()[i] &= ~(CI_TOI | CI_TOICOUNT_MASK);
       toip()[i] = 1.0f;
     }
@@ -1403,7 +1407,7 @@ struct Swarm {
       // ---- per-contact TOI; a body lagging behind the table's alpha0 is advanced first (idempotent per body: all of
       //      its wall contacts advance it to the same target, so the first pass advances, the second computes)
 #pragma unroll 1
-      for (int i = tid; i < nC; i += KB_SWARM_THREADS) {
+      for (int i = tid; i < nC; i += NT) {
         const uint32_t w = cwp()[i];
         const uint32_t pr = cpairp()[i];
         const int pa = (int)(pr & 0xFFFFu);
@@ -1425,7 +1429,7 @@ struct Swarm {
       }
       __syncthreads();
 #pragma unroll 1
-      for (int i = tid; i < nC; i += KB_SWARM_THREADS) {
+      for (int i = tid; i < nC; i += NT) {
         const uint32_t w = cwp()[i];
         const uint32_t pr = cpairp()[i];
         const int pa = (int)(pr & 0xFFFFu), pb = (int)(pr >> 16);
@@ -1453,7 +1457,7 @@ struct Swarm {
       // ---- minimum alpha, first in world-list order (highest index) on ties: key = alpha bits << 32 | ~index
       unsigned long long best = ~0ull;
 #pragma unroll 1
-      for (int i = tid; i < nC; i += KB_SWARM_THREADS) {
+      for (int i = tid; i < nC; i += NT) {
         const uint32_t w = cwp()[i];
         if ((int)(cpairp()[i] & 0xFFFFu) >= nWall) continue;
         const int toiCount = (w & CI_TOICOUNT_MASK) >> CI_TOICOUNT_SHIFT;
@@ -1476,7 +1480,7 @@ struct Swarm {
         misc(17 + 2 * (tid >> 5)) = (uint32_t)(best >> 32);
       }
       __syncthreads();
-      for (int w = 0; w < KB_SWARM_THREADS / 32; ++w) {
+      for (int w = 0; w < NT / 32; ++w) {
         const unsigned long long o = (unsigned long long)(uint32_t)misc(16 + 2 * w) | ((unsigned long long)(uint32_t)misc(17 + 2 * w) << 32);
         best = o < best ? o : best;
       }
@@ -1601,7 +1605,7 @@ struct Swarm {
       synchronizeFixtures(bd);
       // invalidate the cached TOIs of every contact of the displaced body
 #pragma unroll 1
-      for (int i = tid; i < nC; i += KB_SWARM_THREADS) {
+      for (int i = tid; i < nC; i += NT) {
         const uint32_t pr = cpairp()[i];
         if (pbody((int)(pr & 0xFFFFu)) == bd || pbody((int)(pr >> 16)) == bd) cwp()[i] &= ~CI_TOI;
       }
@@ -1643,7 +1647,7 @@ struct Swarm {
     bool bad = false;
     float* flat = a.obsFlat ? a.obsFlat + (size_t)env * (2 * N + L.L) : nullptr;
 #pragma unroll 1
-    for (int b = tid; b < L.B; b += KB_SWARM_THREADS) {
+    for (int b = tid; b < L.B; b += NT) {
       const float4 p = pos4(b);
       bad |= !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
       const float ox = (float)((double)p.x / 25.0), oy = (float)((double)p.y / 25.0);
@@ -1662,7 +1666,7 @@ struct Swarm {
     if (anyBad && tid == 0) hdr(H_STATUS) |= KB_STATUS_NONFINITE;
     if (a.obsLight || flat) {
       const SF64Arr ls = lightState();
-      for (int i = tid; i < L.L; i += KB_SWARM_THREADS) {
+      for (int i = tid; i < L.L; i += NT) {
         const double v = ls[i];
         if (a.obsLight) a.obsLight[(size_t)env * L.L + i] = v;
         if (flat) flat[2 * N + i] = (float)v;
@@ -1700,7 +1704,8 @@ struct Swarm {
 };
 
 // ----------------------------------------------------------------------------------- kernels
-__device__ __forceinline__ void swarmBind(Swarm& s, const KernelArgs& a, int env, int sceneOverride = -1) {
+template <int NT>
+__device__ __forceinline__ void swarmBind(Swarm<NT>& s, const KernelArgs& a, int env, int sceneOverride = -1) {
   s.blob = a.blobs + (size_t)env * a.L.blobWords;
   const int scene = sceneOverride >= 0 ? sceneOverride : (a.envScene ? a.envScene[env] : 0);
   s.px = a.proxies + (size_t)scene * a.L.Pp;
@@ -1708,9 +1713,10 @@ __device__ __forceinline__ void swarmBind(Swarm& s, const KernelArgs& a, int env
   s.nWall = __ldg(&a.scenes[scene].wallEdges);
 }
 
-__global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_step_kernel(const __grid_constant__ KernelArgs a) {
+template <int NT>
+__global__ void __launch_bounds__(NT, NT >= 512 ? 1 : (NT >= 256 ? 2 : 4)) kb_swarm_step_kernel(const __grid_constant__ KernelArgs a) {
   const int env = a.envOffset + blockIdx.x;
-  Swarm s(a.L, a.W);
+  Swarm<NT> s(a.L, a.W);
   swarmBind(s, a, env);
   const int scene = a.envScene ? a.envScene[env] : 0;
   s.loadState();
@@ -1739,16 +1745,17 @@ __global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_step_kernel(cons
 #endif
 }
 
-__global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_reset_kernel(const __grid_constant__ KernelArgs a) {
+template <int NT>
+__global__ void __launch_bounds__(NT, NT >= 512 ? 1 : (NT >= 256 ? 2 : 4)) kb_swarm_reset_kernel(const __grid_constant__ KernelArgs a) {
   const int env = blockIdx.x;
   if (a.mask && !a.mask[env]) return;
   const Layout& L = a.L;
-  Swarm s(a.L, a.W);
+  Swarm<NT> s(a.L, a.W);
   int scene = a.envScene ? a.envScene[env] : 0;
   if (a.sampler) {   // a fresh scene drawn on the device (kb_sample.cuh)
     const uint32_t ep = a.episode[env];
     scene = sampleScene(a.sampler, a.lights, L.numLights > 0 ? L.numLights : 1, L.B, L.M, scene, a.sampler->envIdBase + env, ep,
-                        s.tid, KB_SWARM_THREADS, a.samplePose + (size_t)env * L.B * 3,
+                        s.tid, NT, a.samplePose + (size_t)env * L.B * 3,
                         a.sampleLight + (size_t)env * (L.L > 0 ? L.L : 1), []() { __syncthreads(); });
     if (s.tid == 0) {
       a.episode[env] = ep + 1u;
@@ -1759,8 +1766,8 @@ __global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_reset_kernel(con
   swarmBind(s, a, env, scene);
   const int tid = s.tid;
   uint32_t* bw = reinterpret_cast<uint32_t*>(s.blob);
-  for (int i = tid; i < 2 * KB_NUM_COUNTERS; i += KB_SWARM_THREADS) bw[L.oCnt + i] = 0u;
-  for (int i = tid; i < H_WORDS; i += KB_SWARM_THREADS) s.hdr(i) = 0u;
+  for (int i = tid; i < 2 * KB_NUM_COUNTERS; i += NT) bw[L.oCnt + i] = 0u;
+  for (int i = tid; i < H_WORDS; i += NT) s.hdr(i) = 0u;
   __syncthreads();
   if (tid == 0) {
     s.hdr(H_SCENE) = (uint32_t)scene;
@@ -1771,8 +1778,8 @@ __global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_reset_kernel(con
       ts[3 + KB_EP_SUCCESS] = 0.0;
     }
   }
-  for (int i = tid; i < L.L; i += KB_SWARM_THREADS) s.lightState()[i] = a.lightInit ? a.lightInit[(size_t)env * L.L + i] : 0.0;
-  for (int k = tid; k < L.N; k += KB_SWARM_THREADS) {
+  for (int i = tid; i < L.L; i += NT) s.lightState()[i] = a.lightInit ? a.lightInit[(size_t)env * L.L + i] : 0.0;
+  for (int k = tid; k < L.N; k += NT) {
     double* c = s.ctrl(k);
     const int kind = __ldg(&s.bc[k].kind);
     c[0] = c[1] = c[2] = c[3] = 0.0;
@@ -1783,7 +1790,7 @@ __global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_reset_kernel(con
       c[1] = a.kbVel[((size_t)env * L.N + k) * 2 + 1];
     }
   }
-  for (int b = tid; b <= L.B; b += KB_SWARM_THREADS) {
+  for (int b = tid; b <= L.B; b += NT) {
     if (b < L.B) {
       const double* p = a.pose + ((size_t)env * L.B + b) * 3;
       const float x = (float)(25.0 * p[0]);
@@ -1804,9 +1811,9 @@ __global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_reset_kernel(con
   }
   s.loadConsts(a.lights + (size_t)scene * (L.numLights > 0 ? L.numLights : 1));
   // proxies: b2Fixture::CreateProxies -> fat AABB = aabb -+ aabbExtension, every proxy buffered as moved
-  for (int w = tid; w < a.W.movedWords; w += KB_SWARM_THREADS) s.moved(w) = 0u;
+  for (int w = tid; w < a.W.movedWords; w += NT) s.moved(w) = 0u;
   __syncthreads();
-  for (int p = tid; p < L.P; p += KB_SWARM_THREADS) {
+  for (int p = tid; p < L.P; p += NT) {
     float4 f;
     if (p < s.nWall) {
       const V2 v1 = pvert(s.px + p, 1), v2 = pvert(s.px + p, 2);
@@ -1834,13 +1841,14 @@ __global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_reset_kernel(con
 }
 
 // Body.set_pose (lib/body.py:67-69) -> b2Body::SetTransform on the flagged bodies
-__global__ void __launch_bounds__(KB_SWARM_THREADS, 1) kb_swarm_setpose_kernel(const __grid_constant__ KernelArgs a) {
+template <int NT>
+__global__ void __launch_bounds__(NT, NT >= 512 ? 1 : (NT >= 256 ? 2 : 4)) kb_swarm_setpose_kernel(const __grid_constant__ KernelArgs a) {
   const int env = blockIdx.x;
   const Layout& L = a.L;
-  Swarm s(a.L, a.W);
+  Swarm<NT> s(a.L, a.W);
   swarmBind(s, a, env);
   s.loadState();
-  for (int b = s.tid; b < L.B; b += KB_SWARM_THREADS) {
+  for (int b = s.tid; b < L.B; b += NT) {
     if (a.mask && !a.mask[(size_t)env * L.B + b]) continue;
     const double* p = a.pose + ((size_t)env * L.B + b) * 3;
     const float x = (float)(p[0] * 25.0);

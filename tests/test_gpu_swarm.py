@@ -12,6 +12,9 @@ from parity_util import assert_same_obs, assert_same_state, run_parity
 pytestmark = pytest.mark.gpu
 
 
+SWARM_BLOCKS = (128, 256, 512)   # the swarm tier picks its CTA width from the shared-memory footprint
+
+
 def _tier(nb):
     return nb.launch_config()["block_threads"]
 
@@ -21,7 +24,7 @@ def test_c4_lattice_small(oracle, native, side):
     """64- and 256-kilobot lattices of the C4 scene (the judge's parity bar for the tier)."""
     sc = SC.c4_swarm(4, side=side)
     ob, nb = run_parity(oracle, native, sc, steps=6, actions=np.zeros((6, 4, 2)))
-    assert _tier(nb) == 512
+    assert _tier(nb) in SWARM_BLOCKS
     assert nb.contacts()[1].min() > side * side     # dense persistent contacts
 
 
@@ -41,7 +44,7 @@ def test_corner_jam_both_tiers(oracle, native, force, toi, monkeypatch):
     monkeypatch.setenv("KB_FORCE_SWARM", force)
     sc = SC.swarm_corner(6, n=48, enable_toi=toi)
     ob, nb = run_parity(oracle, native, sc, steps=25)
-    assert _tier(nb) == (512 if force == "1" else 64)
+    assert (_tier(nb) in SWARM_BLOCKS) == (force == "1")
     if toi:
         assert nb.counters()[:, abi.COUNTER_NAMES.index("toi_events")].sum() > 0
 
@@ -63,7 +66,7 @@ def test_swarm_tier_more_than_62_bodies(oracle, native):
     """100 kilobots jammed into the corner: only the swarm tier can run this (the lane-group kernels stop at 62)."""
     sc = SC.swarm_corner(3, n=100, spread=.07)
     ob, nb = run_parity(oracle, native, sc, steps=20)
-    assert _tier(nb) == 512
+    assert _tier(nb) in SWARM_BLOCKS
 
 
 def test_swarm_direct_control_and_kinds(oracle, native, monkeypatch):
