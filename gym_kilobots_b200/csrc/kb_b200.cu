@@ -726,13 +726,22 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     W.oSweep = o; o += 4 * L.Bp;
     L.oToi = o; o += L.Cmax;
     L.oGen = o;
+    const int K = L.Kmax;
+    W.oEnt0 = o; o += K;
+    W.oEntC = o; o += round4((K + 1) / 2);
+    W.oEntI = o; o += round4((K + 1) / 2);
+    W.oRow = o; o += round4((K + 4 + 1) / 2);
+    W.oRec = round4(o); o = W.oRec + 12 * K;
+    W.oTlC = o; o += round4((K + 1) / 2);
+    W.hashSize = 64;
+    W.hashShift = 26;
+    while (W.hashSize < L.Cmax + L.Cmax / 2) { W.hashSize *= 2; W.hashShift -= 1; }   // load factor <= 2/3 at capacity
+    W.oHash = o; o += W.hashSize;
     L.blobWords = round4(o);
     auto al = [](int x, int a) { return (x + a - 1) / a * a; };
     int z = 0;
     W.zPos = z; z += 16 * L.Bp;
     W.zVel = z; z += 16 * L.Bp;
-    W.zQ = z; z += 8 * L.Bp;
-    W.zMI = z; z += 8 * L.Bp;
     W.zHdr = z; z += 4 * H_WORDS;
     W.zMoved = z; z += 4 * W.movedWords;
     z = al(z, 8);
@@ -741,15 +750,9 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     W.zMisc = z; z += 4 * 64;
     W.zIsl = z; z += al(2 * L.Bp, 4);
     W.zIslState = z; z += al(L.Bp, 4);
-    W.zEnt0 = z; z += 4 * L.Kmax;
-    W.zEntC = z; z += al(2 * L.Kmax, 4);
-    W.zEntI = z; z += al(2 * L.Kmax, 4);
-    W.zRow = z; z += al(2 * (L.Kmax + 4), 4);
     z = al(z, 16);
     W.zScr = z;
-    const int K = L.Kmax;
     int q = 0;
-    W.sTlC = q; q += al(2 * K, 4);
     W.sTlB = q; q += 4 * K;
     W.sAdj = q; q += 8 * K;          // two packed entries (list index | other body << 16) per touching contact
     W.sBstart = q; q += al(2 * (L.Bp + 2), 4);
@@ -761,7 +764,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     W.sLastLvl = q; q += al(2 * L.Bp, 4);
     W.sCflag = q; q += al(K, 4);
     W.sLvlCnt = q; q += al(2 * (K + 4), 4);
-    int scratch = std::max(q, 32 * K);
+    int scratch = q;
     W.cWakeAt = 0;
     scratch = std::max(scratch, 4 * L.Bp);
     // uniform grid over the table rectangle (+2 cells of margin), cell = 0.05 m = 1.25 b2 units
@@ -771,11 +774,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     W.gy0 = std::min(s0.wall_y0, s0.wall_y1) - 2.0f * cell;
     W.gx = std::min(256, std::max(1, (int)std::ceil(std::fabs(s0.wall_x1 - s0.wall_x0) / cell) + 4));
     W.gy = std::min(256, std::max(1, (int)std::ceil(std::fabs(s0.wall_y1 - s0.wall_y0) / cell) + 4));
-    W.hashSize = 64;
-    W.hashShift = 26;
-    while (W.hashSize < L.Cmax + L.Cmax / 2) { W.hashSize *= 2; W.hashShift -= 1; }   // load factor <= 2/3 at capacity
     q = 0;
-    W.gHash = q; q += 4 * W.hashSize;
     W.gCellStart = q; q += 4 * (W.gx * W.gy + 2);
     W.gCellCur = q;
     W.gSorted = q; q += al(2 * L.Pp, 4);

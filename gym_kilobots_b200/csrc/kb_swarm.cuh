@@ -62,6 +62,30 @@ namespace kb {
 #define SW_T(i) do { } while (0)
 #endif
 
+// proxies standing in for references into the env's blob (HBM / L2)
+struct GF2 {
+  float2* p;
+  __device__ __forceinline__ operator float2() const { return *p; }
+  __device__ __forceinline__ void operator=(float2 v) const { *p = v; }
+};
+struct GF4 {
+  float4* p;
+  __device__ __forceinline__ operator float4() const { return *p; }
+  __device__ __forceinline__ void operator=(float4 v) const { *p = v; }
+  __device__ __forceinline__ float get(int i) const { return reinterpret_cast<const float*>(p)[i]; }
+  __device__ __forceinline__ void set(int i, float v) const { reinterpret_cast<float*>(p)[i] = v; }
+};
+struct GU32 {
+  uint32_t* p;
+  __device__ __forceinline__ operator uint32_t() const { return *p; }
+  __device__ __forceinline__ uint32_t operator=(uint32_t v) const { *p = v; return v; }
+};
+struct GU16 {
+  uint16_t* p;
+  __device__ __forceinline__ operator uint32_t() const { return (uint32_t)*p; }
+  __device__ __forceinline__ void operator=(uint32_t v) const { *p = (uint16_t)v; }
+};
+
 template <int NT>
 struct Swarm {
   const Layout& L;
@@ -89,18 +113,24 @@ struct Swarm {
   // ---- shared memory (byte offsets from W)
   __device__ __forceinline__ SF4 pos4(int b) const { return SF4{sa + W.zPos + 16u * (uint32_t)b}; }   // cx cy a sleepTime
   __device__ __forceinline__ SF4 vel4(int b) const { return SF4{sa + W.zVel + 16u * (uint32_t)b}; }   // vx vy w flags
-  __device__ __forceinline__ SF2 q2(int b) const { return SF2{sa + W.zQ + 8u * (uint32_t)b}; }        // sin cos
-  __device__ __forceinline__ SF2 mi2(int b) const { return SF2{sa + W.zMI + 8u * (uint32_t)b}; }      // invMass invI
+  // (sin, cos) of the body angle: the q half of the blob's xf4 rows (the static slot B holds (0, 1))
+  __device__ __forceinline__ GF2 q2(int b) const { return GF2{reinterpret_cast<float2*>(blob + L.oXf + 4 * b + 2)}; }
+  __device__ __forceinline__ float2 massOf(int b) const { return make_float2(__ldg(&bc[b].invMass), __ldg(&bc[b].invI)); }
   __device__ __forceinline__ SU32 hdr(int i) const { return SU32{sa + W.zHdr + 4u * (uint32_t)i}; }
   __device__ __forceinline__ SU32 moved(int w) const { return SU32{sa + W.zMoved + 4u * (uint32_t)w}; }
   __device__ __forceinline__ SU32 misc(int i) const { return SU32{sa + W.zMisc + 4u * (uint32_t)i}; }
   __device__ __forceinline__ SU16 isl(int b) const { return SU16{sa + W.zIsl + 2u * (uint32_t)b}; }
   __device__ __forceinline__ uint32_t islStateAddr(int i) const { return sa + W.zIslState + (uint32_t)i; }
-  __device__ __forceinline__ SU32 ent0(int e) const { return SU32{sa + W.zEnt0 + 4u * (uint32_t)e}; }  // bA | bB << 16
-  __device__ __forceinline__ SU16 entC(int e) const { return SU16{sa + W.zEntC + 2u * (uint32_t)e}; }  // contact index
-  __device__ __forceinline__ SU16 entI(int e) const { return SU16{sa + W.zEntI + 2u * (uint32_t)e}; }  // island | fast << 15
-  __device__ __forceinline__ SU16 rowStart(int l) const { return SU16{sa + W.zRow + 2u * (uint32_t)l}; }
-  __device__ __forceinline__ SF4 rec4(int i) const { return SF4{sa + W.zScr + 16u * (uint32_t)i}; }
+  // the level schedule and the solver's records live in the blob (L2-resident, streamed by warp 0 level by level): that
+  // keeps the CTA's shared memory small enough for TWO CTAs per SM at 1024 kilobots, and a second CTA overlaps perfectly
+  __device__ __forceinline__ GU32 ent0(int e) const { return GU32{reinterpret_cast<uint32_t*>(blob + W.oEnt0) + e}; }        // bA | bB << 16
+  __device__ __forceinline__ GU16 entC(int e) const { return GU16{reinterpret_cast<uint16_t*>(blob + W.oEntC) + e}; }        // contact index
+  __device__ __forceinline__ GU16 entI(int e) const { return GU16{reinterpret_cast<uint16_t*>(blob + W.oEntI) + e}; }        // island | fast << 15
+  __device__ __forceinline__ GU16 rowStart(int l) const { return GU16{reinterpret_cast<uint16_t*>(blob + W.oRow) + l}; }
+  // three float4 per schedule entry: two phase-dependent records and the masses (invMassA, invIA, invMassB, invIB)
+  __device__ __forceinline__ GF4 rec4(int i) const { return GF4{reinterpret_cast<float4*>(blob + W.oRec) + i}; }
+  __device__ __forceinline__ uint16_t* tlCp() const { return reinterpret_cast<uint16_t*>(blob + W.oTlC); }
+  __device__ __forceinline__ uint32_t* hashp() const { return reinterpret_cast<uint32_t*>(blob + W.oHash); }
   __device__ __forceinline__ SF64Arr lightState() const { return SF64Arr{sa + W.zLight}; }
   __device__ __forceinline__ LCs lightConst(int l) const { return LCs{sa + W.zLc + 4u * LC_WORDS * (uint32_t)l}; }
   // scratch views (alias the record region; each is live only inside the phase that names it)
@@ -164,20 +194,15 @@ struct Swarm {
   __device__ __forceinline__ void loadState() {
     const float4* bp = reinterpret_cast<const float4*>(blob + L.oPos);
     const float4* bv = reinterpret_cast<const float4*>(blob + L.oVel);
-    const float4* bx = reinterpret_cast<const float4*>(blob + L.oXf);
 #pragma unroll 1
     for (int b = tid; b <= L.B; b += NT) {
       if (b < L.B) {
         pos4(b) = bp[b];
         vel4(b) = bv[b];
-        const float4 x = bx[b];
-        q2(b) = make_float2(x.z, x.w);
-        mi2(b) = make_float2(__ldg(&bc[b].invMass), __ldg(&bc[b].invI));
       } else {
         pos4(b) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         vel4(b) = make_float4(0.0f, 0.0f, 0.0f, u2f(BF_AWAKE));
         q2(b) = make_float2(0.0f, 1.0f);
-        mi2(b) = make_float2(0.0f, 0.0f);
       }
     }
     const uint32_t* bw = reinterpret_cast<const uint32_t*>(blob);
@@ -199,10 +224,9 @@ struct Swarm {
 #pragma unroll 1
     for (int b = tid; b < L.B; b += NT) {
       const float4 p = pos4(b);
-      const float2 q = q2(b);
       bp[b] = p;
       bv[b] = vel4(b);
-      bx[b] = make_float4(p.x, p.y, q.x, q.y);
+      reinterpret_cast<float2*>(bx + b)[0] = make_float2(p.x, p.y);   // xf.p == c (zero local centres); xf.q is kept in place
     }
     uint32_t* bw = reinterpret_cast<uint32_t*>(blob);
     for (int i = tid; i < H_WORDS; i += NT) bw[L.oHdr + i] = hdr(i);
@@ -607,7 +631,7 @@ struct Swarm {
     const int type = (int)(f2u(r1.z) & 0xFFu);
     const float radiusA = __ldg(&px[pa].radius), radiusB = __ldg(&px[pb].radius);
     const float4 cA4 = pos4(bA), cB4 = pos4(bB);
-    const float2 kA = mi2(bA), kB = mi2(bB);
+    const float2 kA = massOf(bA), kB = massOf(bB);
     const float mA = kA.x, iA = kA.y, mB = kB.x, iB = kB.y;
     const V2 cA = mk(cA4.x, cA4.y), cB = mk(cB4.x, cB4.y);
     Xf xfA, xfB;
@@ -644,14 +668,15 @@ struct Swarm {
     const float rnB = cross(rB, normal);
     const float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
     const float nMass = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
-    rec4(2 * e) = make_float4(normal.x, normal.y, nMass, r1.x);
-    rec4(2 * e + 1) = make_float4(rA.x, rA.y, rB.x, rB.y);
+    rec4(3 * e) = make_float4(normal.x, normal.y, nMass, r1.x);
+    rec4(3 * e + 1) = make_float4(rA.x, rA.y, rB.x, rB.y);
+    rec4(3 * e + 2) = make_float4(mA, iA, mB, iB);
   }
   __device__ __forceinline__ void warmStartSimple(int e) const {
     const uint32_t bb = ent0(e);
     const int bA = (int)(bb & 0xFFFFu), bB = (int)(bb >> 16);
-    const float4 r0 = rec4(2 * e), r1 = rec4(2 * e + 1);
-    const float2 kA = mi2(bA), kB = mi2(bB);
+    const float4 r0 = rec4(3 * e), r1 = rec4(3 * e + 1), r2 = rec4(3 * e + 2);
+    const float2 kA = make_float2(r2.x, r2.y), kB = make_float2(r2.z, r2.w);
     float4 vA = vel4(bA), vB = vel4(bB);
     const V2 normal = mk(r0.x, r0.y);
     const V2 tangent = cross(normal, 1.0f);
@@ -669,8 +694,8 @@ struct Swarm {
   __device__ __forceinline__ void solveVelocitySimple(int e) const {
     const uint32_t bb = ent0(e);
     const int bA = (int)(bb & 0xFFFFu), bB = (int)(bb >> 16);
-    const float4 r0 = rec4(2 * e), r1 = rec4(2 * e + 1);
-    const float2 kA = mi2(bA), kB = mi2(bB);
+    const float4 r0 = rec4(3 * e), r1 = rec4(3 * e + 1), r2 = rec4(3 * e + 2);
+    const float2 kA = make_float2(r2.x, r2.y), kB = make_float2(r2.z, r2.w);
     float4 a4 = vel4(bA), b4 = vel4(bB);
     const V2 normal = mk(r0.x, r0.y);
     const V2 rA0 = mk(r1.x, r1.y), rB0 = mk(r1.z, r1.w);
@@ -690,18 +715,18 @@ struct Swarm {
     b4.x = Bv2.x; b4.y = Bv2.y;
     if (bA != S) vel4(bA) = a4;
     vel4(bB) = b4;
-    rec4(2 * e).set(3, newImpulse);
+    rec4(3 * e).set(3, newImpulse);
   }
   // b2ContactSolver::StoreImpulses, then the position-phase records
   __device__ __forceinline__ void storeSimple(int e) const {
     const int ci = (int)entC(e);
     float* rec = recp(ci);
-    rec[SR_IMP] = rec4(2 * e).get(3);
+    rec[SR_IMP] = rec4(3 * e).get(3);
     const float4 r0 = reinterpret_cast<const float4*>(rec)[0];
     const uint32_t tp = f2u(rec[SR_TYPE]) & 0xFFu;
     const uint32_t pr = cpairp()[ci];
-    rec4(2 * e) = r0;
-    rec4(2 * e + 1) = make_float4(__ldg(&px[pr & 0xFFFFu].radius), __ldg(&px[pr >> 16].radius), u2f(tp), 0.0f);
+    rec4(3 * e) = r0;
+    rec4(3 * e + 1) = make_float4(__ldg(&px[pr & 0xFFFFu].radius), __ldg(&px[pr >> 16].radius), u2f(tp), 0.0f);
     const int bA = (int)(ent0(e) & 0xFFFFu);
     // kilobot against kilobot: circle manifold, local point zero, local centres zero (no rotation matters)
     if (tp == MANIFOLD_CIRCLES && bA != S && r0.z == 0.0f && r0.w == 0.0f) entI(e) = (uint32_t)entI(e) | 0x8000u;
@@ -710,8 +735,8 @@ struct Swarm {
   __device__ __forceinline__ bool solvePositionSimple(int e, bool fast, float baumgarte, float limit, bool skipZero) const {
     const uint32_t bb = ent0(e);
     const int bA = (int)(bb & 0xFFFFu), bB = (int)(bb >> 16);
-    const float4 r1 = rec4(2 * e + 1);
-    const float2 kA = mi2(bA), kB = mi2(bB);
+    const float4 r1 = rec4(3 * e + 1), r2 = rec4(3 * e + 2);
+    const float2 kA = make_float2(r2.x, r2.y), kB = make_float2(r2.z, r2.w);
     const float mA = kA.x, iA = kA.y, mB = kB.x, iB = kB.y;
     float4 pA4 = pos4(bA), pB4 = pos4(bB);
     V2 cA = mk(pA4.x, pA4.y), cB = mk(pB4.x, pB4.y);
@@ -723,7 +748,7 @@ struct Swarm {
       point = 0.5f * (cA + cB);
       separation = dot(cB - cA, normal) - r1.x - r1.y;
     } else {
-      const float4 r0 = rec4(2 * e);
+      const float4 r0 = rec4(3 * e);
       const V2 ln = mk(r0.x, r0.y), lp = mk(r0.z, r0.w);
       const int type = (int)f2u(r1.z);
       // no body of this tier has a local centre or a local manifold point on B: rotations multiply exact zeros
@@ -775,7 +800,8 @@ struct Swarm {
   __device__ __forceinline__ void solve() {
     const int nC = (int)hdr(H_NC);
     const int B = L.B;
-    const uint32_t tlC = scr(W.sTlC), tlB = scr(W.sTlB), adj = scr(W.sAdj), bstart = scr(W.sBstart), bcur = scr(W.sBcur);
+    uint16_t* const tlC = tlCp();
+    const uint32_t tlB = scr(W.sTlB), adj = scr(W.sAdj), bstart = scr(W.sBstart), bcur = scr(W.sBcur);
     const uint32_t ordT = scr(W.sOrd), ordL = scr(W.sOlvl), ordI = scr(W.sOisl), stack = scr(W.sStack);
     const uint32_t lastLvl = scr(W.sLastLvl), cflag = scr(W.sCflag), lvlCnt = scr(W.sLvlCnt);
     // ---- touching list in world-list order (descending contact index)
@@ -805,7 +831,7 @@ struct Swarm {
       int total;
       const int dst = K + blockExScan(t ? 1 : 0, &total);
       if (t && dst < L.Kmax) {
-        sts_u16(tlC + 2u * (uint32_t)dst, (uint32_t)i);
+        tlC[dst] = (uint16_t)i;
         sts_u32(tlB + 4u * (uint32_t)dst, bodies);
       }
       K += total;
@@ -963,7 +989,7 @@ struct Swarm {
       const int l = (int)lds_u16(ordL + 2u * (uint32_t)p);
       const uint32_t e = atomicAddU16(lvlCnt, l);
       ent0((int)e) = lds_u32(tlB + 4u * (uint32_t)t);
-      entC((int)e) = lds_u16(tlC + 2u * (uint32_t)t);
+      entC((int)e) = (uint32_t)tlC[t];
       entI((int)e) = lds_u16(ordI + 2u * (uint32_t)p);
     }
 #pragma unroll 1
@@ -1176,17 +1202,17 @@ struct Swarm {
     const int k = (int)floorf((c - origin) * W.invCell);
     return k < 0 ? 0 : (k >= n ? n - 1 : k);
   }
-  __device__ __forceinline__ bool hashHas(uint32_t table, uint32_t key) const {
+  __device__ __forceinline__ bool hashHas(const uint32_t* table, uint32_t key) const {
     uint32_t h = (key * 2654435761u) >> W.hashShift;
     for (;;) {
-      const uint32_t k = lds_u32(table + 4u * h);
+      const uint32_t k = __ldcg(table + h);   // filled by atomics at L2: read there
       if (k == key) return true;
       if (k == 0u) return false;
       h = (h + 1u) & (uint32_t)(W.hashSize - 1);
     }
   }
   // candidate test for the ordered pair (i < j), both dynamic proxies; fi = fat AABB of i
-  __device__ __forceinline__ bool newPair(uint32_t table, int i, int j, const float4& fi, bool movedI) const {
+  __device__ __forceinline__ bool newPair(const uint32_t* table, int i, int j, const float4& fi, bool movedI) const {
     if (!movedI && !isMoved(j)) return false;
     const float4 fj = fatp()[j];
     const bool overlap = !(fj.x - fi.z > 0.0f || fj.y - fi.w > 0.0f || fi.x - fj.z > 0.0f || fi.y - fj.w > 0.0f);
@@ -1201,11 +1227,12 @@ struct Swarm {
     for (int w = tid; w < W.movedWords; w += NT) any |= (uint32_t)moved(w) != 0u;
     if (__syncthreads_or(any) == 0) return;
     int nC = (int)hdr(H_NC);
-    const uint32_t table = scr(W.gHash), cellStart = scr(W.gCellStart), cellCur = scr(W.gCellCur), sorted = scr(W.gSorted);
+    uint32_t* const table = hashp();
+    const uint32_t cellStart = scr(W.gCellStart), cellCur = scr(W.gCellCur), sorted = scr(W.gSorted);
     const uint32_t pcnt = scr(W.gPcnt);
     const int ncell = W.gx * W.gy;
     // ---- hash of the existing pairs; cell counts
-    for (int i = tid; i < W.hashSize; i += NT) sts_u32(table + 4u * (uint32_t)i, 0u);
+    for (int i = tid; i < W.hashSize; i += NT) table[i] = 0u;
     for (int c = tid; c <= ncell; c += NT) sts_u32(cellStart + 4u * (uint32_t)c, 0u);
     __syncthreads();
 #pragma unroll 1
@@ -1215,8 +1242,7 @@ struct Swarm {
       const uint32_t key = ((pa < pb ? pa : pb) << 16 | (pa < pb ? pb : pa)) + 1u;
       uint32_t h = (key * 2654435761u) >> W.hashShift;
       for (;;) {
-        uint32_t old;
-        asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(table + 4u * h), "r"(0u), "r"(key) : "memory");
+        const uint32_t old = atomicCAS(table + h, 0u, key);
         if (old == 0u || old == key) break;
         h = (h + 1u) & (uint32_t)(W.hashSize - 1);
       }
@@ -1551,8 +1577,9 @@ struct Swarm {
             const float* rec = recp(ci);
             const float4 r0 = reinterpret_cast<const float4*>(rec)[0];
             const uint32_t pr = cpairp()[ci];
-            rec4(2 * k) = r0;
-            rec4(2 * k + 1) = make_float4(__ldg(&px[pr & 0xFFFFu].radius), __ldg(&px[pr >> 16].radius),
+            rec4(3 * k) = r0;
+            rec4(3 * k + 2) = make_float4(0.0f, 0.0f, massOf(bd).x, massOf(bd).y);   // the table against the kilobot
+            rec4(3 * k + 1) = make_float4(__ldg(&px[pr & 0xFFFFu].radius), __ldg(&px[pr >> 16].radius),
                                           u2f(f2u(rec[SR_TYPE]) & 0xFFu), 0.0f);
           }
           for (int it = 0; it < 20; ++it) {
@@ -1570,7 +1597,7 @@ struct Swarm {
           }
           for (int k = 0; k < nIsland; ++k) {
             initSimple(k);
-            rec4(2 * k).set(3, 0.0f);   // no warm starting
+            rec4(3 * k).set(3, 0.0f);   // no warm starting
           }
           for (int it = 0; it < L.velIters; ++it)
             for (int k = 0; k < nIsland; ++k) solveVelocitySimple(k);
@@ -1800,13 +1827,11 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : (NT >= 256 ? 2 : 4)) kb_sw
       s.pos4(b) = make_float4(x, y, ang, 0.0f);
       s.vel4(b) = make_float4(0.0f, 0.0f, 0.0f, u2f(BF_AWAKE));
       s.q2(b) = make_float2(q.s, q.c);
-      s.mi2(b) = make_float2(__ldg(&s.bc[b].invMass), __ldg(&s.bc[b].invI));
       s.sweepp()[b] = make_float4(x, y, ang, 0.0f);
     } else {
       s.pos4(b) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       s.vel4(b) = make_float4(0.0f, 0.0f, 0.0f, u2f(BF_AWAKE));
       s.q2(b) = make_float2(0.0f, 1.0f);
-      s.mi2(b) = make_float2(0.0f, 0.0f);
     }
   }
   s.loadConsts(a.lights + (size_t)scene * (L.numLights > 0 ? L.numLights : 1));

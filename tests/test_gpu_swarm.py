@@ -116,22 +116,24 @@ def test_swarm_masked_reset_set_pose_and_resume(oracle, native):
         assert_same_obs(ref[t - 6], nb.step(acts[t]), "swarm: resume, step %d" % t)
 
 
-def test_largest_swarms_fit_by_shrinking_the_capacities(oracle, native):
-    """1521 kilobots in one env: kb_create shrinks the contact / solver capacities until the CTA's image fits the SM
-    (never below 5B + 32 pairs / 2B + 32 touching contacts); 2025 do not fit and are refused."""
-    sc = SC.c4_swarm(1, side=39)
-    ob = oracle.OracleBatch(sc.scenes, 1, sc.env_scene, sc.max_contacts)
-    nb = native.NativeBatch(sc.scenes, 1, sc.env_scene, sc.max_contacts)
-    ob.reset(sc.body_pose, sc.light_state)
-    nb.reset(sc.body_pose, sc.light_state)
-    oo, on = ob.step(np.zeros((1, 2))), nb.step(np.zeros((1, 2)))
-    assert np.array_equal(oo["kilobots"], on["kilobots"]) and np.array_equal(ob.bodies(), nb.bodies())
-    (po, no), (pn, nn) = ob.contacts(), nb.contacts()
-    assert np.array_equal(no, nn) and np.array_equal(po[:, :no[0]], pn[:, :no[0]])     # capacities differ, lists do not
-    assert nb.N == 1521 and nb.C < ob.C and nb.launch_config()["smem_bytes_per_block"] <= 232448
-    assert not nb.get_status().any()
-    with pytest.raises(RuntimeError, match="does not fit"):
-        big = SC.c4_swarm(1, side=45)
+def test_largest_swarms(oracle, native):
+    """1521 and 1681 kilobots in one env (the 2.0 x 1.5 m table holds a 41 x 41 lattice) (the schedule, the solver records and the pair hash live in the env's L2-resident
+    blob, so the CTA's shared-memory image is ~35 bytes per body + ~21 per touching contact: everything up to the tier's
+    2040-body limit fits); 2116 are refused."""
+    for side in (39, 41):
+        sc = SC.c4_swarm(1, side=side)
+        ob = oracle.OracleBatch(sc.scenes, 1, sc.env_scene, sc.max_contacts)
+        nb = native.NativeBatch(sc.scenes, 1, sc.env_scene, sc.max_contacts)
+        ob.reset(sc.body_pose, sc.light_state)
+        nb.reset(sc.body_pose, sc.light_state)
+        oo, on = ob.step(np.zeros((1, 2))), nb.step(np.zeros((1, 2)))
+        assert np.array_equal(oo["kilobots"], on["kilobots"]) and np.array_equal(ob.bodies(), nb.bodies())
+        (po, no), (pn, nn) = ob.contacts(), nb.contacts()
+        assert np.array_equal(no, nn) and np.array_equal(po[:, :no[0]], pn[:, :no[0]])
+        assert nb.N == side * side and nb.launch_config()["smem_bytes_per_block"] <= 232448
+        assert not nb.get_status().any()
+    with pytest.raises(RuntimeError, match="2040"):
+        big = SC.c4_swarm(1, side=46)
         native.NativeBatch(big.scenes, 1)
 
 
