@@ -751,6 +751,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     W.zIsl = z; z += al(2 * L.Bp, 4);
     W.zIslState = z; z += al(L.Bp, 4);
     z = al(z, 16);
+    W.zDummy = z; z += 16 * 32;      // one row per lane: what the idle lanes of the solver relay load from and store to
     W.zScr = z;
     int q = 0;
     W.sTlB = q; q += 4 * K;

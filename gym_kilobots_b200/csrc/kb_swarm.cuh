@@ -116,6 +116,7 @@ struct Swarm {
   // (sin, cos) of the body angle: the q half of the blob's xf4 rows (the static slot B holds (0, 1))
   __device__ __forceinline__ GF2 q2(int b) const { return GF2{reinterpret_cast<float2*>(blob + L.oXf + 4 * b + 2)}; }
   __device__ __forceinline__ float2 massOf(int b) const { return make_float2(__ldg(&bc[b].invMass), __ldg(&bc[b].invI)); }
+  __device__ __forceinline__ SF4 dummy4() const { return SF4{sa + W.zDummy + 16u * (uint32_t)(tid & 31)}; }
   __device__ __forceinline__ SU32 hdr(int i) const { return SU32{sa + W.zHdr + 4u * (uint32_t)i}; }
   __device__ __forceinline__ SU32 moved(int w) const { return SU32{sa + W.zMoved + 4u * (uint32_t)w}; }
   __device__ __forceinline__ SU32 misc(int i) const { return SU32{sa + W.zMisc + 4u * (uint32_t)i}; }
@@ -672,12 +673,13 @@ struct Swarm {
     rec4(3 * e + 1) = make_float4(rA.x, rA.y, rB.x, rB.y);
     rec4(3 * e + 2) = make_float4(mA, iA, mB, iB);
   }
-  __device__ __forceinline__ void warmStartSimple(int e) const {
-    const uint32_t bb = ent0(e);
-    const int bA = (int)(bb & 0xFFFFu), bB = (int)(bb >> 16);
-    const float4 r0 = rec4(3 * e), r1 = rec4(3 * e + 1), r2 = rec4(3 * e + 2);
+  // The *Core forms take the schedule entry and the records as values: the relay (below) fetches them from L2 ahead of
+  // the warp's turn, so that only the shared-memory traffic on the bodies and the arithmetic are on the critical path.
+  // (sA / sB: the two bodies' vel4 or pos4 rows; wA / wB: where the results go -- the same rows, or the dummy row when body A
+  //  is the table or when the lane only keeps step with its warp)
+  __device__ __forceinline__ void warmStartCore(SF4 sA, SF4 sB, SF4 wA, SF4 wB, const float4& r0, const float4& r1, const float4& r2) const {
     const float2 kA = make_float2(r2.x, r2.y), kB = make_float2(r2.z, r2.w);
-    float4 vA = vel4(bA), vB = vel4(bB);
+    float4 vA = sA, vB = sB;
     const V2 normal = mk(r0.x, r0.y);
     const V2 tangent = cross(normal, 1.0f);
     const V2 rA = mk(r1.x, r1.y), rB = mk(r1.z, r1.w);
@@ -688,15 +690,18 @@ struct Swarm {
     vB.z += kB.y * cross(rB, P);
     vB.x = vB.x + kB.x * P.x;
     vB.y = vB.y + kB.x * P.y;
-    if (bA != S) vel4(bA) = vA;
-    vel4(bB) = vB;
+    wA = vA;
+    wB = vB;
   }
-  __device__ __forceinline__ void solveVelocitySimple(int e) const {
+  __device__ __forceinline__ void warmStartSimple(int e) const {
     const uint32_t bb = ent0(e);
-    const int bA = (int)(bb & 0xFFFFu), bB = (int)(bb >> 16);
-    const float4 r0 = rec4(3 * e), r1 = rec4(3 * e + 1), r2 = rec4(3 * e + 2);
+    const SF4 sA = vel4((int)(bb & 0xFFFFu)), sB = vel4((int)(bb >> 16));
+    warmStartCore(sA, sB, (int)(bb & 0xFFFFu) != S ? sA : dummy4(), sB, rec4(3 * e), rec4(3 * e + 1), rec4(3 * e + 2));
+  }
+  // returns the accumulated normal impulse (the caller keeps it in rec4(3e).w)
+  __device__ __forceinline__ float solveVelocityCore(SF4 sA, SF4 sB, SF4 wA, SF4 wB, const float4& r0, const float4& r1, const float4& r2) const {
     const float2 kA = make_float2(r2.x, r2.y), kB = make_float2(r2.z, r2.w);
-    float4 a4 = vel4(bA), b4 = vel4(bB);
+    float4 a4 = sA, b4 = sB;
     const V2 normal = mk(r0.x, r0.y);
     const V2 rA0 = mk(r1.x, r1.y), rB0 = mk(r1.z, r1.w);
     const V2 Av = mk(a4.x, a4.y), Bv = mk(b4.x, b4.y);
@@ -713,9 +718,14 @@ struct Swarm {
     b4.z += kB.y * cross(rB0, P);
     a4.x = Av2.x; a4.y = Av2.y;
     b4.x = Bv2.x; b4.y = Bv2.y;
-    if (bA != S) vel4(bA) = a4;
-    vel4(bB) = b4;
-    rec4(3 * e).set(3, newImpulse);
+    wA = a4;
+    wB = b4;
+    return newImpulse;
+  }
+  __device__ __forceinline__ void solveVelocitySimple(int e) const {
+    const uint32_t bb = ent0(e);
+    const SF4 sA = vel4((int)(bb & 0xFFFFu)), sB = vel4((int)(bb >> 16));
+    rec4(3 * e).set(3, solveVelocityCore(sA, sB, (int)(bb & 0xFFFFu) != S ? sA : dummy4(), sB, rec4(3 * e), rec4(3 * e + 1), rec4(3 * e + 2)));
   }
   // b2ContactSolver::StoreImpulses, then the position-phase records
   __device__ __forceinline__ void storeSimple(int e) const {
@@ -733,12 +743,19 @@ struct Swarm {
   }
   // one constraint of b2ContactSolver::SolvePositionConstraints (baumgarte / limit are the regular or the TOI ones)
   __device__ __forceinline__ bool solvePositionSimple(int e, bool fast, float baumgarte, float limit, bool skipZero) const {
+    float4 r0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (!fast) r0 = rec4(3 * e);
     const uint32_t bb = ent0(e);
-    const int bA = (int)(bb & 0xFFFFu), bB = (int)(bb >> 16);
-    const float4 r1 = rec4(3 * e + 1), r2 = rec4(3 * e + 2);
+    const SF4 sA = pos4((int)(bb & 0xFFFFu)), sB = pos4((int)(bb >> 16));
+    return solvePositionCore(sA, sB, (int)(bb & 0xFFFFu) != S ? sA : dummy4(), sB, fast, r0, rec4(3 * e + 1), rec4(3 * e + 2), baumgarte,
+                             limit, skipZero);
+  }
+  // (r0 is only read when !fast)
+  __device__ __forceinline__ bool solvePositionCore(SF4 sA, SF4 sB, SF4 wA, SF4 wB, bool fast, const float4& r0, const float4& r1,
+                                                    const float4& r2, float baumgarte, float limit, bool skipZero) const {
     const float2 kA = make_float2(r2.x, r2.y), kB = make_float2(r2.z, r2.w);
     const float mA = kA.x, iA = kA.y, mB = kB.x, iB = kB.y;
-    float4 pA4 = pos4(bA), pB4 = pos4(bB);
+    float4 pA4 = sA, pB4 = sB;
     V2 cA = mk(pA4.x, pA4.y), cB = mk(pB4.x, pB4.y);
     V2 normal, point;
     float separation;
@@ -748,7 +765,6 @@ struct Swarm {
       point = 0.5f * (cA + cB);
       separation = dot(cB - cA, normal) - r1.x - r1.y;
     } else {
-      const float4 r0 = rec4(3 * e);
       const V2 ln = mk(r0.x, r0.y), lp = mk(r0.z, r0.w);
       const int type = (int)f2u(r1.z);
       // no body of this tier has a local centre or a local manifold point on B: rotations multiply exact zeros
@@ -787,13 +803,41 @@ struct Swarm {
     pA4.z -= iA * cross(rA, P);
     cB = cB + mB * P;
     pB4.z += iB * cross(rB, P);
-    if (bA != S) {
-      pA4.x = cA.x; pA4.y = cA.y;
-      pos4(bA) = pA4;
-    }
+    pA4.x = cA.x; pA4.y = cA.y;
+    wA = pA4;
     pB4.x = cB.x; pB4.y = cB.y;
-    pos4(bB) = pB4;
+    wB = pB4;
     return ok;
+  }
+
+  // ---- relay: the warps of the CTA take the levels of the schedule in turn, RG levels per turn (turn k = rows RG k ..
+  // RG k + RG - 1 belongs to warp k mod NR; the rows of a turn sit in lane groups of RL lanes and are solved one after the
+  // other).  A warp fetches its turn's schedule entries and records from L2 while the NR - 1 turns before it are being
+  // solved, waits for its predecessor on a named barrier (id 1 + warp; 32 arriving + 32 waiting threads), does the
+  // shared-memory part and hands over.  An entry is always solved by the same thread, so its accumulated impulse is
+  // thread-private.  (A level wider than RL entries is several rows of the schedule.)
+  static constexpr int NR = NT / 32 < 8 ? NT / 32 : 8;
+  static constexpr int RG = 4, RL = 32 / RG;
+  __device__ __forceinline__ void relayWait(int w) const {
+    __syncwarp();
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + w) : "memory");
+  }
+  __device__ __forceinline__ void relayPass(int w) const {
+    __syncwarp();   // the warp's shared-memory stores are all issued before it arrives
+    asm volatile("bar.arrive %0, 64;" ::"r"(1 + w) : "memory");
+  }
+  // turn order inside one pass over the turns 0..nTurns-1, repeated without a block-wide barrier in between
+  __device__ __forceinline__ void relayEnter(int wid, int k, int nTurns, bool firstTurn) const {
+    if (firstTurn) return;
+    const int prev = (k == 0 ? nTurns - 1 : k - 1) % NR;
+    if (prev != wid) relayWait(wid);
+    else __syncwarp();
+  }
+  __device__ __forceinline__ void relayLeave(int wid, int k, int nTurns, bool lastTurn) const {
+    if (lastTurn) return;
+    const int next = (k == nTurns - 1 ? 0 : k + 1) % NR;
+    if (next != wid) relayPass(next);
+    else __syncwarp();
   }
 
   // b2World::Solve
@@ -961,25 +1005,30 @@ struct Swarm {
     SW_T(4);
     nIsl += (uint32_t)nIslDfs + lonelyCount;
     nLvl += (uint32_t)maxL;
-    // ---- rows: rowStart[l] = first schedule entry of level l (exclusive scan of the level counts), then scatter
+    // ---- rows: the entries of a level, cut into rows of at most RL (the entries of one level touch disjoint dynamic bodies:
+    // their order cannot influence any result, so a wide level may be solved as several rows one after the other).
+    // rowStart[r] = first schedule entry of row r, rowStart[nRows] = nOrd; the level's first entry is the scatter cursor.
 #pragma unroll 1
     for (int p = tid; p < nOrd; p += NT) atomicAddU16(lvlCnt, (int)lds_u16(ordL + 2u * (uint32_t)p));
     __syncthreads();
+    int nRows = 0;
     {
       int run = 0;
 #pragma unroll 1
       for (int base = 1; base <= maxL + 1; base += NT) {
         const int l = base + tid;
         const int c = l <= maxL ? (int)lds_u16(lvlCnt + 2u * (uint32_t)l) : 0;
-        int total;
+        int total, rtotal;
         const int off = run + blockExScan(c, &total);
+        const int nr = (c + RL - 1) / RL;
+        const int row = nRows + blockExScan(nr, &rtotal);
         __syncthreads();
-        if (l <= maxL + 1) {
-          rowStart(l) = (uint32_t)off;
-          sts_u16(lvlCnt + 2u * (uint32_t)l, (uint32_t)off);   // scatter cursor
-        }
+        if (l <= maxL + 1) sts_u16(lvlCnt + 2u * (uint32_t)l, (uint32_t)off);   // scatter cursor
+        for (int j = 0; j < nr; ++j) rowStart(row + j) = (uint32_t)(off + j * RL);
         run += total;
+        nRows += rtotal;
       }
+      if (tid == 0) rowStart(nRows) = (uint32_t)nOrd;
       __syncthreads();
     }
     // entries of one level touch disjoint dynamic bodies: their order within the level cannot influence any result
@@ -1017,24 +1066,56 @@ struct Swarm {
     nPts += (uint32_t)nOrd;
     __syncthreads();
     SW_T(5);
-    // ---- warm start + velocity iterations: warp 0 walks the levels
-    // (a software-pipelined variant that fetched the next level's entry, records and masses ahead was measured
-    //  slower: a single warp pays ~5 cycles per issued instruction, so instruction count, not load latency, is the cost)
-    if (tid < 32) {
-      int s0 = (int)rowStart(1);
-      for (int l = 1; l <= maxL; ++l) {
-        const int s1 = (int)rowStart(l + 1);
-        for (int e = s0 + tid; e < s1; e += 32) warmStartSimple(e);
-        __syncwarp();
-        s0 = s1;
-      }
-      for (int it = 0; it < L.velIters; ++it) {
-        s0 = (int)rowStart(1);
-        for (int l = 1; l <= maxL; ++l) {
-          const int s1 = (int)rowStart(l + 1);
-          for (int e = s0 + tid; e < s1; e += 32) solveVelocitySimple(e);
-          __syncwarp();
-          s0 = s1;
+    // ---- warm start (pass 0) + velocity iterations: the relay over the levels
+    const int nTurns = (nRows + RG - 1) / RG;
+    {
+      const int lane = tid & 31, wid = tid >> 5;
+      const int g = lane / RL, li = lane % RL;
+      const int passes = 1 + L.velIters;
+      if (wid < NR) {
+        for (int pass = 0; pass < passes; ++pass) {
+#pragma unroll 1
+          for (int k = wid; k < nTurns; k += NR) {
+            const int row = RG * k + g;
+            int s0 = 0, s1 = 0;
+            if (row < nRows) {
+              s0 = (int)rowStart(row);
+              s1 = (int)rowStart(row + 1);
+            }
+            const int e = s0 + li;
+            const bool mine = e < s1;
+            const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float4 r0 = z4, r1 = z4, r2 = z4;
+            const SF4 dm = dummy4();
+            SF4 sA = dm, sB = dm, wA = dm;
+            if (mine) {
+              const uint32_t bb = ent0(e);
+              r0 = rec4(3 * e);
+              r1 = rec4(3 * e + 1);
+              r2 = rec4(3 * e + 2);
+              sA = vel4((int)(bb & 0xFFFFu));
+              sB = vel4((int)(bb >> 16));
+              if ((int)(bb & 0xFFFFu) != S) wA = sA;
+            }
+            relayEnter(wid, k, nTurns, pass == 0 && k == 0);
+            // the levels of the turn, one after the other: every lane runs every step (no branches on the way), the lanes
+            // outside the step's group on the dummy row
+            float imp = 0.0f;
+#pragma unroll
+            for (int gg = 0; gg < RG; ++gg) {
+              const bool act = g == gg;
+              const SF4 a = act ? sA : dm, b = act ? sB : dm, c = act ? wA : dm;
+              if (pass == 0) {
+                warmStartCore(a, b, c, b, r0, r1, r2);
+              } else {
+                const float ni = solveVelocityCore(a, b, c, b, r0, r1, r2);
+                imp = act ? ni : imp;
+              }
+              __syncwarp();
+            }
+            relayLeave(wid, k, nTurns, pass == passes - 1 && k == nTurns - 1);
+            if (mine && pass != 0) rec4(3 * e).set(3, imp);
+          }
         }
       }
     }
@@ -1071,20 +1152,63 @@ struct Swarm {
     //      below -3 linearSlop seen in this sweep)
     nPit += (uint32_t)nIslDfs + lonelyCount;   // first iteration of every island (a lonely island is solved by it)
     for (int it = 0; it < L.posIters; ++it) {
-      if (tid < 32) {
-        int s0 = (int)rowStart(1);
-        for (int l = 1; l <= maxL; ++l) {
-          const int s1 = (int)rowStart(l + 1);
-          for (int e = s0 + tid; e < s1; e += 32) {
-            const uint32_t ei = entI(e);
-            const int island = (int)(ei & 0x7FFFu);
-            if ((lds_u8(islStateAddr(island)) & 1u) != 0u) {
-              const bool ok = solvePositionSimple(e, (ei & 0x8000u) != 0u, KB_BAUMGARTE, -3.0f * KB_LINEAR_SLOP, true);
-              if (!ok) sts_u8(islStateAddr(island), 3u);
+      {
+        const int lane = tid & 31, wid = tid >> 5;
+        const int g = lane / RL, li = lane % RL;
+        if (wid < NR) {
+#pragma unroll 1
+          for (int k = wid; k < nTurns; k += NR) {
+            const int row = RG * k + g;
+            int s0 = 0, s1 = 0;
+            if (row < nRows) {
+              s0 = (int)rowStart(row);
+              s1 = (int)rowStart(row + 1);
             }
+            const int e = s0 + li;
+            uint32_t ei = 0x8000u;
+            const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float4 r0 = z4, r1 = z4, r2 = z4;
+            const SF4 dm = dummy4();
+            SF4 sA = dm, sB = dm, wA = dm;
+            bool mine = e < s1;
+            if (mine) {
+              ei = entI(e);
+              // (bit 0 of the island's state does not change during a sweep)
+              mine = (lds_u8(islStateAddr((int)(ei & 0x7FFFu))) & 1u) != 0u;
+            }
+            if (mine) {
+              const uint32_t bb = ent0(e);
+              if ((ei & 0x8000u) == 0u) r0 = rec4(3 * e);
+              r1 = rec4(3 * e + 1);
+              r2 = rec4(3 * e + 2);
+              sA = pos4((int)(bb & 0xFFFFu));
+              sB = pos4((int)(bb >> 16));
+              if ((int)(bb & 0xFFFFu) != S) wA = sA;
+            } else {
+              ei = 0x8000u;   // keeps step on the dummy row: the circle-circle form, coincident centres, no correction
+            }
+            relayEnter(wid, k, nTurns, k == 0);
+#ifdef KB_PROFILE
+            const long long tr1 = clock64();
+#endif
+#pragma unroll
+            for (int gg = 0; gg < RG; ++gg) {
+              const bool act = g == gg;
+              const SF4 a = act ? sA : dm, b = act ? sB : dm, c = act ? wA : dm;
+              const bool ok = solvePositionCore(a, b, c, b, (ei & 0x8000u) != 0u, r0, r1, r2, KB_BAUMGARTE, -3.0f * KB_LINEAR_SLOP, true);
+              if (!ok && act && mine) sts_u8(islStateAddr((int)(ei & 0x7FFFu)), 3u);
+              __syncwarp();
+            }
+#ifdef KB_PROFILE
+            const long long tr2 = clock64();
+#endif
+            relayLeave(wid, k, nTurns, k == nTurns - 1);
+#ifdef KB_PROFILE
+            tp[14] += tr2 - tr1;             // (position relay, warp 0: cycles of its turns' work / cycles handing over)
+            tp[15] += clock64() - tr2;
+            tp[13] += 1000;                  // (turns of warp 0, in thousands, on top of the ~5 kcycles of gather + store)
+#endif
           }
-          __syncwarp();
-          s0 = s1;
         }
       }
       __syncthreads();

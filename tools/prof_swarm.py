@@ -15,7 +15,7 @@ CSRC = os.path.join(ROOT, "gym_kilobots_b200", "csrc")
 PROF = os.path.join(ROOT, "build", "lib_prof.so")
 NAMES = ["sense/light", "collide", "touching list", "body lists (CSR)", "island DFS (thread 0)", "rows+integrate+init",
          "warm start + velocity", "store + integrate", "position", "transform + sleep", "sync fixtures", "find new contacts",
-         "toi", "gather + store", "-", "-"]
+         "toi", "gather + store", "(position relay, warp 0: work of its turns)", "(position relay, warp 0: handing over)"]
 
 if sys.argv[1] == "build":
     os.makedirs(os.path.dirname(PROF), exist_ok=True)
@@ -38,16 +38,21 @@ nb.reset(sc.body_pose, sc.light_state)
 lib = native._lib
 lib.kb_get_profile.argtypes = [C.c_void_p, C.c_void_p]
 acts = np.zeros((T, E, 2))
+cprev = nb.counters().astype(np.float64)
 for t in range(T):
     nb.step(acts[t])
-    if t in (0, T // 2, T - 1):
+    if t not in (0, T // 2, T - 1):
+        cprev = nb.counters().astype(np.float64)
+    else:
         prof = np.zeros((E, 16), np.uint64)
         lib.kb_get_profile(nb.h, prof.ctypes.data_as(C.c_void_p))
         p = prof.astype(np.float64)
-        tot = p.sum(1)
-        c = nb.counters().astype(np.float64)
-        print("env-step %d: %.2f Mcycles per env-step (mean; max %.2f); touching/substep %.0f, levels/substep %.0f" % (
-            t, tot.mean() / 1e6, tot.max() / 1e6, c[:, 2].sum() / c[:, 0].sum(), c[:, 3].sum() / c[:, 0].sum()))
+        tot = p[:, :14].sum(1)
+        cnow = nb.counters().astype(np.float64)
+        c = cnow - cprev
+        cprev = cnow
+        print("env-step %d: %.2f Mcycles per env-step (mean; max %.2f); touching/substep %.0f, levels/substep %.0f, position sweeps x islands/substep %.1f, islands/substep %.1f" % (
+            t, tot.mean() / 1e6, tot.max() / 1e6, c[:, 2].sum() / c[:, 0].sum(), c[:, 3].sum() / c[:, 0].sum(), c[:, 4].sum() / c[:, 0].sum(), c[:, 7].sum() / c[:, 0].sum()))
         for i, n in enumerate(NAMES):
             if p[:, i].mean() > 0:
                 print("   %-28s %9.0f kcycles  %5.1f %%" % (n, p[:, i].mean() / 1e3, 100 * p[:, i].mean() / tot.mean()))
