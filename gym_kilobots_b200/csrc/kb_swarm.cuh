@@ -1184,8 +1184,6 @@ struct Swarm {
               sA = pos4((int)(bb & 0xFFFFu));
               sB = pos4((int)(bb >> 16));
               if ((int)(bb & 0xFFFFu) != S) wA = sA;
-            } else {
-              ei = 0x8000u;   // keeps step on the dummy row: the circle-circle form, coincident centres, no correction
             }
             relayEnter(wid, k, nTurns, k == 0);
 #ifdef KB_PROFILE
@@ -1193,10 +1191,11 @@ struct Swarm {
 #endif
 #pragma unroll
             for (int gg = 0; gg < RG; ++gg) {
-              const bool act = g == gg;
-              const SF4 a = act ? sA : dm, b = act ? sB : dm, c = act ? wA : dm;
-              const bool ok = solvePositionCore(a, b, c, b, (ei & 0x8000u) != 0u, r0, r1, r2, KB_BAUMGARTE, -3.0f * KB_LINEAR_SLOP, true);
-              if (!ok && act && mine) sts_u8(islStateAddr((int)(ei & 0x7FFFu)), 3u);
+              // (here one guard is cheaper than running the idle lanes on the dummy row: the sqrt / division paths diverge)
+              if (g == gg && mine) {
+                const bool ok = solvePositionCore(sA, sB, wA, sB, (ei & 0x8000u) != 0u, r0, r1, r2, KB_BAUMGARTE, -3.0f * KB_LINEAR_SLOP, true);
+                if (!ok) sts_u8(islStateAddr((int)(ei & 0x7FFFu)), 3u);
+              }
               __syncwarp();
             }
 #ifdef KB_PROFILE
