@@ -199,6 +199,7 @@ PRODUCT_ONLY = {
     "set_sampler": (C.c_int, [_VP, C.POINTER(KbSampleSpec)]),
     "reset_sampled": (C.c_int, [_VP, _VP, _VP]),
     "get_sampled": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "selftest_exact_math": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
 }
 
 

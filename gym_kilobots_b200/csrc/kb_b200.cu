@@ -1619,6 +1619,73 @@ int kb_flat_observation_dim(const KbHandle* hh) {
   return 2 * h->L.N + h->L.L + 4 * h->L.M;
 }
 
+// ---- arithmetic self-test (kb_sqrt / kb_rcp / kb_div against the plain operators) -----------------------------
+}  // extern "C"
+namespace kb {
+__device__ __forceinline__ uint32_t mixBits(uint32_t x) {   // (murmur3 finaliser: a bijection of the 32-bit words)
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool sameFloat(float a, float b) {
+  return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b);
+}
+__global__ void kb_selftest_math_kernel(int divRounds, unsigned long long* mismatches) {
+  unsigned long long bad0 = 0ull, bad1 = 0ull, bad2 = 0ull, taken = 0ull;
+  const unsigned long long total = 1ull << 32;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t u = (uint32_t)i;
+    const float x = __uint_as_float(u);
+    {
+      bool out = false;
+      const float y = kb_sqrt_u(x, out);
+      if (!out && !sameFloat(y, sqrtf(x))) ++bad0;
+      if (!out) ++taken;
+      out = false;
+      const float z = kb_rcp_u(x, out);
+      if (!out && !sameFloat(z, 1.0f / x)) ++bad1;
+      if (!out) ++taken;
+    }
+    for (int r = 0; r < divRounds; ++r) {
+      uint32_t ua = mixBits(u ^ (0x9e3779b9u * (uint32_t)(2 * r + 1))), ub = mixBits(~u + 0x7f4a7c15u * (uint32_t)(r + 1));
+      if ((r & 1) != 0) {   // both exponents inside the fast path's window
+        ua = (ua & 0x807fffffu) | ((64u + ((ua >> 23) & 0xFFu) % 127u) << 23);
+        ub = (ub & 0x807fffffu) | ((64u + ((ub >> 23) & 0xFFu) % 127u) << 23);
+      }
+      const float a = __uint_as_float(ua), b = __uint_as_float(ub);
+      bool out = false;
+      const float q = kb_div_u(a, b, out);
+      if (!out && !sameFloat(q, a / b)) ++bad2;
+      if (!out) ++taken;
+    }
+  }
+  if (bad0) atomicAdd(mismatches + 0, bad0);
+  if (bad1) atomicAdd(mismatches + 1, bad1);
+  if (bad2) atomicAdd(mismatches + 2, bad2);
+  atomicAdd(mismatches + 3, taken);
+}
+}  // namespace kb
+extern "C" {
+int kb_selftest_exact_math(int32_t device, int32_t div_rounds_log2, uint64_t* mismatches) {
+  using namespace kb;
+  if (!mismatches || div_rounds_log2 < 0 || div_rounds_log2 > 6) return fail(KB_ERR_INVALID, "kb_selftest_exact_math: invalid arguments");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) {
+    cudaGetLastError();
+    return fail(KB_ERR_NO_DEVICE, "kb_selftest_exact_math: no CUDA device");
+  }
+  if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 4 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(d, 0, 4 * sizeof(unsigned long long)));
+  kb_selftest_math_kernel<<<148 * 8, 256>>>(1 << div_rounds_log2, d);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(mismatches, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaFree(d));
+  return KB_OK;
+}
+
 // ---- off-screen rasteriser (kb_render.cuh) ---------------------------------------------------------------
 int kb_render(KbHandle* hh, const int32_t* env_ids, int32_t num_images, int32_t width, int32_t height, uint8_t* rgb,
               void* stream) {

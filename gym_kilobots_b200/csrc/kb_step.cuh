@@ -884,32 +884,18 @@ struct Sim {
     const int bA = IT_BA(item), bB = IT_BB(item);
     const float4 r1 = rec4(2 * e + 1);
     const float4 kA = bc4(bA), kB = bc4(bB);
-    float4 pA4 = pos4(bA), pB4 = pos4(bB);
-    const float mA = kA.x, iA = kA.y, mB = kB.x, iB = kB.y;
-    V2 cA = mk(pA4.x, pA4.y), cB = mk(pB4.x, pB4.y);
-    V2 normal = cB - cA;
-    normalize(normal);
-    const V2 point = 0.5f * (cA + cB);
-    const float separation = dot(cB - cA, normal) - r1.x - r1.y;
-    const bool ok = separation >= -3.0f * KB_LINEAR_SLOP;
-    const float C = b2clamp(KB_BAUMGARTE * (separation + KB_LINEAR_SLOP), -KB_MAX_LINEAR_CORRECTION, 0.0f);
-    if (C == 0.0f) return ok;
-    const V2 rA = point - cA;
-    const V2 rB = point - cB;
-    const float rnA = cross(rA, normal);
-    const float rnB = cross(rB, normal);
-    const float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-    const float impulse = K > 0.0f ? -C / K : 0.0f;
-    const V2 P = impulse * normal;
-    cA = cA - mA * P;
-    pA4.z -= iA * cross(rA, P);
-    cB = cB + mB * P;
-    pB4.z += iB * cross(rB, P);
-    pA4.x = cA.x; pA4.y = cA.y;
-    pos4(bA) = pA4;
-    if (bB != S) {
-      pB4.x = cB.x; pB4.y = cB.y;
-      pos4(bB) = pB4;
+    const float4 pA4 = pos4(bA), pB4 = pos4(bB);
+    float4 a1, b1;
+    bool moved, bad = false;
+    bool ok = kb_position_pair_t<false>(pA4, pB4, r1.x, r1.y, kA.x, kA.y, kB.x, kB.y, KB_BAUMGARTE, -3.0f * KB_LINEAR_SLOP, true, a1,
+                                        b1, moved, bad);
+    if (moved) {
+      pos4(bA) = a1;
+      if (bB != S) pos4(bB) = b1;
+    }
+    if (__builtin_expect(bad, 0)) {   // (off the dependent chain: the rows are stored already)
+      ok = kb_position_pair_cold(pos4(bA).a, bB != S ? pos4(bB).a : 0u, pA4, pB4, r1.x, r1.y, kA.x, kA.y, kB.x, kB.y, KB_BAUMGARTE,
+                                 -3.0f * KB_LINEAR_SLOP, true);
     }
     return ok;
   }

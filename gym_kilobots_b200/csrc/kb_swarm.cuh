@@ -756,15 +756,23 @@ struct Swarm {
     const float2 kA = make_float2(r2.x, r2.y), kB = make_float2(r2.z, r2.w);
     const float mA = kA.x, iA = kA.y, mB = kB.x, iB = kB.y;
     float4 pA4 = sA, pB4 = sB;
+    if (fast) {
+      float4 a1, b1;
+      bool moved, bad = false;
+      bool okf = kb_position_pair_t<false>(pA4, pB4, r1.x, r1.y, mA, iA, mB, iB, baumgarte, limit, skipZero, a1, b1, moved, bad);
+      if (moved) {
+        wA = a1;
+        wB = b1;
+      }
+      if (__builtin_expect(bad, 0)) {   // (off the dependent chain: the rows are stored already)
+        okf = kb_position_pair_cold(wA.a, wB.a, pA4, pB4, r1.x, r1.y, mA, iA, mB, iB, baumgarte, limit, skipZero);
+      }
+      return okf;
+    }
     V2 cA = mk(pA4.x, pA4.y), cB = mk(pB4.x, pB4.y);
     V2 normal, point;
     float separation;
-    if (fast) {
-      normal = cB - cA;
-      normalize(normal);
-      point = 0.5f * (cA + cB);
-      separation = dot(cB - cA, normal) - r1.x - r1.y;
-    } else {
+    {
       const V2 ln = mk(r0.x, r0.y), lp = mk(r0.z, r0.w);
       const int type = (int)f2u(r1.z);
       // no body of this tier has a local centre or a local manifold point on B: rotations multiply exact zeros

@@ -339,6 +339,14 @@ int kb_flat_observation_dim(const KbHandle* h);
 int kb_render(KbHandle* h, const int32_t* env_ids, int32_t num_images, int32_t width, int32_t height,
               uint8_t* rgb, void* stream);
 
+/* Self-test of the kernels' arithmetic (no reference counterpart; see kb_sqrt_u / kb_rcp_u / kb_div_u in
+ * csrc/kb_types.cuh): the straight-line square root and reciprocal are compared with sqrtf(x) and 1.0f / x on all 2^32
+ * float bit patterns, the division with a / b on 2^(32 + div_rounds_log2) pseudo-random pairs (half of them with both
+ * operands inside the fast path's exponent window); inputs the forms hand back to the plain operators are skipped.
+ * mismatches: host u64[4] = differing results of (sqrt, reciprocal, division) and the number of comparisons made;
+ * bit-exact parity with Box2D's x86-64 arithmetic needs the first three to be 0.  device < 0: the current device. */
+int kb_selftest_exact_math(int32_t device, int32_t div_rounds_log2, uint64_t* mismatches);
+
 #ifdef __cplusplus
 }
 #endif
