@@ -762,8 +762,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     W.sOlvl = q; q += al(2 * K, 4);
     W.sOisl = q; q += al(2 * K, 4);
     W.sStack = q; q += al(2 * L.Bp, 4);
-    W.sLastLvl = q; q += al(2 * L.Bp, 4);
-    W.sCflag = q; q += al(K, 4);
+    W.sBw = q; q += 4 * L.Bp;
     W.sLvlCnt = q; q += al(2 * (K + 4), 4);
     int scratch = q;
     W.cWakeAt = 0;

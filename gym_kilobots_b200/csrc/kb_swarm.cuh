@@ -855,15 +855,14 @@ struct Swarm {
     uint16_t* const tlC = tlCp();
     const uint32_t tlB = scr(W.sTlB), adj = scr(W.sAdj), bstart = scr(W.sBstart), bcur = scr(W.sBcur);
     const uint32_t ordT = scr(W.sOrd), ordL = scr(W.sOlvl), ordI = scr(W.sOisl), stack = scr(W.sStack);
-    const uint32_t lastLvl = scr(W.sLastLvl), cflag = scr(W.sCflag), lvlCnt = scr(W.sLvlCnt);
+    // per-body word of the island search: last level (16 bits) | DW_INISLAND | DW_POPPED | DW_AWAKE
+    const uint32_t bw = scr(W.sBw), lvlCnt = scr(W.sLvlCnt);
+    constexpr uint32_t DW_INISLAND = 1u << 16, DW_POPPED = 1u << 17, DW_AWAKE = 1u << 18;
     // ---- touching list in world-list order (descending contact index)
 #pragma unroll 1
     for (int b = tid; b <= B + 1; b += NT) {
       sts_u16(bstart + 2u * (uint32_t)b, 0u);
-      if (b <= B) {
-        sts_u16(lastLvl + 2u * (uint32_t)b, 0u);
-        isl(b) = SW_NOISLAND;
-      }
+      if (b <= B) isl(b) = SW_NOISLAND;
     }
     __syncthreads();
     int K = 0;
@@ -902,7 +901,6 @@ struct Swarm {
       const int bA = (int)(bb & 0xFFFFu), bB = (int)(bb >> 16);
       if (bA != S) atomicAddU16(bstart, bA + 1);
       if (bB != S) atomicAddU16(bstart, bB + 1);
-      sts_u8(cflag + (uint32_t)t, 0u);
     }
 #pragma unroll 1
     for (int l = tid; l <= K + 1; l += NT) sts_u16(lvlCnt + 2u * (uint32_t)l, 0u);
@@ -948,10 +946,13 @@ struct Swarm {
         }
         sts_u32(adj + 4u * (uint32_t)(j + 1), v);
       }
-      if (s1 == s0 && awake(b)) {   // an island of its own (b2World::Solve seeds it and finds nothing to add)
+      const bool aw = awake(b);
+      const bool lonely = s1 == s0 && aw;
+      if (lonely) {   // an island of its own (b2World::Solve seeds it and finds nothing to add)
         isl(b) = SW_LONELY;
         lonelyCount += 1u;
       }
+      sts_u32(bw + 4u * (uint32_t)b, (aw ? DW_AWAKE : 0u) | (lonely ? DW_INISLAND : 0u));
     }
     {
       int total;
@@ -962,28 +963,39 @@ struct Swarm {
     SW_T(3);
     // ---- thread 0: island DFS (b2World::Solve) in Box2D's order + dependency level of every constraint:
     // level = 1 + max(level of the earlier constraints that share a dynamic body); the static table never links levels.
-    // The popped body's own level stays in a register (its partners are distinct bodies in this tier).
+    // A lone thread pays every shared-memory round trip in full, so the search reads ONE word per partner body (its last
+    // level and its flags; a contact is new exactly when the partner has not been popped yet, which is what Box2D's
+    // per-contact island flag says) and fetches the next contact edge and its partner's word while the current one is
+    // worked off (the partners of one body are distinct bodies, so nothing fetched ahead can change underneath).
     if (tid == 0) {
       int nOrd = 0, nIslands = 0, maxL = 0;
       for (int seed = B - 1; seed >= 0; --seed) {   // body list order: newest (highest index) first
-        if ((uint32_t)isl(seed) != SW_NOISLAND) continue;
-        if (!awake(seed)) continue;
+        const uint32_t ws = lds_u32(bw + 4u * (uint32_t)seed);
+        if ((ws & DW_INISLAND) != 0u || (ws & DW_AWAKE) == 0u) continue;
         int sp = 0;
         sts_u16(stack, (uint32_t)seed);
         sp = 1;
         isl(seed) = (uint32_t)nIslands;
+        sts_u32(bw + 4u * (uint32_t)seed, ws | DW_INISLAND);
         while (sp > 0) {
           const int b = (int)lds_u16(stack + 2u * (uint32_t)(--sp));
           const int s0 = (int)lds_u16(bstart + 2u * (uint32_t)b), s1 = (int)lds_u16(bstart + 2u * (uint32_t)(b + 1));
-          uint32_t lb = lds_u16(lastLvl + 2u * (uint32_t)b);
-          if (!awake(b)) wake(b);
+          const uint32_t wb = lds_u32(bw + 4u * (uint32_t)b);
+          uint32_t lb = wb & 0xFFFFu;
+          if ((wb & DW_AWAKE) == 0u) wake(b);
+          // two edges in flight: en0 / wo0 = the current edge and its partner's word, en1 = the next edge
+          uint32_t en0 = s0 < s1 ? lds_u32(adj + 4u * (uint32_t)s0) : 0u;
+          uint32_t en1 = s0 + 1 < s1 ? lds_u32(adj + 4u * (uint32_t)(s0 + 1)) : 0u;
+          uint32_t wo0 = (s0 < s1 && (en0 >> 16) != (uint32_t)S) ? lds_u32(bw + 4u * (en0 >> 16)) : 0u;
           for (int k = s0; k < s1; ++k) {
-            const uint32_t en = lds_u32(adj + 4u * (uint32_t)k);
+            const uint32_t en = en0, wo = wo0;
+            en0 = en1;
+            wo0 = (k + 1 < s1 && (en0 >> 16) != (uint32_t)S) ? lds_u32(bw + 4u * (en0 >> 16)) : 0u;
+            en1 = k + 2 < s1 ? lds_u32(adj + 4u * (uint32_t)(k + 2)) : 0u;
             const uint32_t t = en & 0xFFFFu, o = en >> 16;
-            if (lds_u8(cflag + t) != 0u) continue;
-            sts_u8(cflag + t, 1u);
-            uint32_t lo = 0u;
-            if (o != (uint32_t)S) lo = lds_u16(lastLvl + 2u * o);
+            const bool dyn = o != (uint32_t)S;
+            if (dyn && (wo & DW_POPPED) != 0u) continue;   // added when the partner was popped
+            const uint32_t lo = dyn ? (wo & 0xFFFFu) : 0u;
             const uint32_t l = (lb > lo ? lb : lo) + 1u;
             lb = l;
             sts_u16(ordT + 2u * (uint32_t)nOrd, t);
@@ -991,16 +1003,16 @@ struct Swarm {
             sts_u16(ordI + 2u * (uint32_t)nOrd, (uint32_t)nIslands);
             ++nOrd;
             maxL = max(maxL, (int)l);
-            if (o != (uint32_t)S) {
-              sts_u16(lastLvl + 2u * o, l);
-              if ((uint32_t)isl((int)o) == SW_NOISLAND) {
+            if (dyn) {
+              sts_u32(bw + 4u * o, (wo & ~0xFFFFu) | l | DW_INISLAND);
+              if ((wo & DW_INISLAND) == 0u) {
                 isl((int)o) = (uint32_t)nIslands;
                 sts_u16(stack + 2u * (uint32_t)sp, o);
                 ++sp;
               }
             }
           }
-          sts_u16(lastLvl + 2u * (uint32_t)b, lb);
+          sts_u32(bw + 4u * (uint32_t)b, lb | DW_INISLAND | DW_POPPED | DW_AWAKE);
         }
         ++nIslands;
       }
