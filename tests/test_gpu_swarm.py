@@ -36,6 +36,31 @@ def test_c4_full_size(oracle, native):
     assert ct.min() > 2000 and pr[:, :, 2].sum(1).min() > 800
 
 
+def test_c4_deep_schedule_replicas(oracle, native):
+    """The relay solver under load: 300 copies of one 1024-kilobot env (two CTAs per SM on every SM), 12 env-steps into
+    the compressing lattice where the level schedule is ~900 rows deep.  Every copy must stay bit-identical to copy 0
+    (a lost hand-over or a stale prefetch in any CTA would show), and copy 0 to the oracle."""
+    E, T = 300, 12
+    one = SC.c4_swarm(1)
+    sc = SC.c4_swarm(E)
+    sc.body_pose[:] = one.body_pose[0]
+    sc.light_state[:] = one.light_state[0]
+    nb = native.NativeBatch(sc.scenes, E, sc.env_scene, sc.max_contacts)
+    ob = oracle.OracleBatch(one.scenes, 1, one.env_scene, one.max_contacts)
+    nb.reset(sc.body_pose, sc.light_state)
+    ob.reset(one.body_pose, one.light_state)
+    for t in range(T):
+        on, oo = nb.step(np.zeros((E, 2))), ob.step(np.zeros((1, 2)))
+        assert np.array_equal(on["kilobots"], np.broadcast_to(on["kilobots"][:1], on["kilobots"].shape)), "copies differ at step %d" % t
+        assert np.array_equal(on["kilobots"][:1], oo["kilobots"]), "copy 0 differs from the oracle at step %d" % t
+    bodies = nb.bodies()
+    assert np.array_equal(bodies, np.broadcast_to(bodies[:1], bodies.shape)) and np.array_equal(bodies[:1], ob.bodies())
+    cn = nb.counters()
+    assert np.array_equal(cn, np.broadcast_to(cn[:1], cn.shape))
+    assert cn[0, 3] / cn[0, 0] > 400          # hundreds of Gauss-Seidel levels per sub-step
+    assert not nb.get_status().any()
+
+
 @pytest.mark.parametrize("force", ["0", "1"])
 @pytest.mark.parametrize("toi", [True, False])
 def test_corner_jam_both_tiers(oracle, native, force, toi, monkeypatch):
