@@ -860,6 +860,45 @@ struct Sim {
     rec4(2 * e).set(3, newImpulse);
   }
 
+  // the same two with the entry's records (r0, r1), inverse masses kk = (mA, iA, mB, iB) and body rows in registers
+  __device__ __forceinline__ void warmStartCached(SF4 rowA, SF4 rowB, const float4& r0, const float4& r1, const float4& kk) {
+    float4 vA = rowA, vB = rowB;
+    const V2 normal = mk(r0.x, r0.y);
+    const V2 tangent = cross(normal, 1.0f);
+    const V2 rA = mk(r1.x, r1.y), rB = mk(r1.z, r1.w);
+    const V2 P = r0.w * normal + 0.0f * tangent;
+    vA.z -= kk.y * cross(rA, P);
+    vA.x = vA.x - kk.x * P.x;
+    vA.y = vA.y - kk.x * P.y;
+    vB.z += kk.w * cross(rB, P);
+    vB.x = vB.x + kk.z * P.x;
+    vB.y = vB.y + kk.z * P.y;
+    rowA = vA;
+    rowB = vB;
+  }
+  __device__ __forceinline__ float solveVelocityCached(SF4 rowA, SF4 rowB, const float4& r0, const float4& r1, const float4& kk) {
+    float4 a4 = rowA, b4 = rowB;
+    const V2 normal = mk(r0.x, r0.y);
+    const V2 rA0 = mk(r1.x, r1.y), rB0 = mk(r1.z, r1.w);
+    const V2 Av = mk(a4.x, a4.y), Bv = mk(b4.x, b4.y);
+    V2 dv = Bv + cross(b4.z, rB0) - Av - cross(a4.z, rA0);
+    float vn = dot(dv, normal);
+    float ni = r0.w;
+    float lambda = -r0.z * (vn - 0.0f);
+    float newImpulse = b2max(ni + lambda, 0.0f);
+    lambda = newImpulse - ni;
+    V2 P = lambda * normal;
+    const V2 Av2 = Av - kk.x * P;
+    a4.z -= kk.y * cross(rA0, P);
+    const V2 Bv2 = Bv + kk.z * P;
+    b4.z += kk.w * cross(rB0, P);
+    a4.x = Av2.x; a4.y = Av2.y;
+    b4.x = Bv2.x; b4.y = Bv2.y;
+    rowA = a4;
+    rowB = b4;
+    return newImpulse;
+  }
+
   // b2ContactSolver::StoreImpulses, then re-purpose the records for the position solver
   __device__ __forceinline__ void storeSimple(int e, int ci, uint32_t item) {
     float* rec = manifoldRec(ci);
@@ -1609,36 +1648,63 @@ struct Sim {
     }
     g.usync();
     KB_T(4);
-    // warm start, then velocity iterations: a lane walks its entries in row order
+    // warm start, then velocity iterations: a lane walks its entries in row order.  Its FIRST entry (slot 0: e == lane,
+    // the lowest row the lane has) stays in registers for all 1 + velIters passes when it is a simple constraint --
+    // records, inverse masses, the two bodies' rows and the accumulated impulse: a row-step of slot 0 is two loads, the
+    // arithmetic and two stores.  Measured: C5 (4 lanes per env) 183.5 -> 193.1 M kilobot-steps/s, C3 (32 lanes) 38.6 -> 40.4 M,
+    // but C2 (8 lanes: rows that mix slot-0 and second entries run both bodies) 1.035 -> 1.046 ms, so the 8- and 16-lane
+    // kernels keep every entry on the ordinary path; folding the two bodies into one (operands selected) lost on all three.
     {
-      int k = g.lane;
-      uint32_t item = k < nOrd ? ent(k) : IT_NONE;
-      for (int r = 0; r < nRowsU; ++r) {
-        if (IT_ROW(item) == r) {
-          const uint32_t cur = item;
-          const int kc = k;
-          k += LPE;
-          item = k < nOrd ? ent(k) : IT_NONE;  // next entry of this lane: fetched while the current one is solved
-          if ((cur & IT_GEN) != 0u) warmStartGeneralNI(*this, genSlot(kc));
-          else warmStartSimple(kc, cur);
-        }
-        g.usync();
+      constexpr bool SLOT0 = LPE == 4 || LPE == 32;
+      const uint32_t it0 = (SLOT0 && g.lane < nOrd) ? ent(g.lane) : IT_NONE;
+      const bool c0 = SLOT0 && it0 != IT_NONE && (it0 & IT_GEN) == 0u;
+      const int row0 = c0 ? IT_ROW(it0) : -1;
+      const int kFirst = c0 ? g.lane + LPE : g.lane;   // the entries walked the ordinary way
+      float4 q0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), q1 = q0, kk = q0;
+      SF4 vA{0u}, vB{0u};
+      if (c0) {
+        q0 = rec4(2 * g.lane);
+        q1 = rec4(2 * g.lane + 1);
+        const float4 kA = bc4(IT_BA(it0)), kB = bc4(IT_BB(it0));
+        kk = make_float4(kA.x, kA.y, kB.x, kB.y);
+        vA = vel4(IT_BA(it0));
+        vB = vel4(IT_BB(it0));
       }
-    }
-    for (int it = 0; it < L.velIters; ++it) {
-      int k = g.lane;
-      uint32_t item = k < nOrd ? ent(k) : IT_NONE;
-      for (int r = 0; r < nRowsU; ++r) {
-        if (IT_ROW(item) == r) {
-          const uint32_t cur = item;
-          const int kc = k;
-          k += LPE;
-          item = k < nOrd ? ent(k) : IT_NONE;
-          if ((cur & IT_GEN) != 0u) solveVelocityGeneralNI(*this, genSlot(kc));
-          else solveVelocitySimple(kc, cur);
+      {
+        int k = kFirst;
+        uint32_t item = k < nOrd ? ent(k) : IT_NONE;
+        for (int r = 0; r < nRowsU; ++r) {
+          if (r == row0) {
+            warmStartCached(vA, vB, q0, q1, kk);
+          } else if (IT_ROW(item) == r) {
+            const uint32_t cur = item;
+            const int kc = k;
+            k += LPE;
+            item = k < nOrd ? ent(k) : IT_NONE;  // next entry of this lane: fetched while the current one is solved
+            if ((cur & IT_GEN) != 0u) warmStartGeneralNI(*this, genSlot(kc));
+            else warmStartSimple(kc, cur);
+          }
+          g.usync();
         }
-        g.usync();
       }
+      for (int it = 0; it < L.velIters; ++it) {
+        int k = kFirst;
+        uint32_t item = k < nOrd ? ent(k) : IT_NONE;
+        for (int r = 0; r < nRowsU; ++r) {
+          if (r == row0) {
+            q0.w = solveVelocityCached(vA, vB, q0, q1, kk);
+          } else if (IT_ROW(item) == r) {
+            const uint32_t cur = item;
+            const int kc = k;
+            k += LPE;
+            item = k < nOrd ? ent(k) : IT_NONE;
+            if ((cur & IT_GEN) != 0u) solveVelocityGeneralNI(*this, genSlot(kc));
+            else solveVelocitySimple(kc, cur);
+          }
+          g.usync();
+        }
+      }
+      if (c0) rec4(2 * g.lane).set(3, q0.w);   // the accumulated impulse, for storeSimple
     }
     KB_T(5);
 #pragma unroll 1
