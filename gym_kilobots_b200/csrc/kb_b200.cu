@@ -1663,6 +1663,61 @@ __global__ void kb_selftest_math_kernel(int divRounds, unsigned long long* misma
   if (bad2) atomicAdd(mismatches + 2, bad2);
   atomicAdd(mismatches + 3, taken);
 }
+// The position solver's kilobot-kilobot step the way the kernels run it -- straight-line pass, rows stored, out-of-line exact
+// pass if a range test fired -- against the plain-operator template on 2^26 pseudo-random pairs of bodies: ordinary
+// overlaps and separations, coincident and nearly coincident centres (zero / denormal squared distances), huge
+// coordinates (infinite squared distance), separations within a few ulps of the slop (tiny corrections), zero and huge
+// inverse masses.  mismatches[4] counts differing rows or verdicts, mismatches[5] the cases that took the exact pass.
+__global__ void kb_selftest_pair_kernel(unsigned long long* mismatches) {
+  __shared__ float4 rows[2 * 256];
+  unsigned long long bad = 0ull, cold = 0ull;
+  const uint32_t wA = (uint32_t)__cvta_generic_to_shared(&rows[2 * threadIdx.x]), wB = wA + 16u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (1u << 26); i += gridDim.x * blockDim.x) {
+    const uint32_t h0 = mixBits(i * 2u + 1u), h1 = mixBits(h0 ^ 0x68bc21ebu), h2 = mixBits(h1 + 0x02e5be93u), h3 = mixBits(h2 ^ i);
+    const float ux = (float)(h0 & 0xFFFFu) * (1.0f / 65536.0f), uy = (float)(h0 >> 16) * (1.0f / 65536.0f);
+    const float ang = 6.2831853f * (float)(h1 & 0xFFFFu) * (1.0f / 65536.0f);
+    const int kind = (int)(h1 >> 16) & 15;
+    float dist = 0.5f + 0.4f * (float)(h2 & 0xFFFFu) * (1.0f / 65536.0f);     // radii 0.4125 each: |.| around the contact
+    float scale = 1.0f;
+    if (kind == 0) dist = 0.0f;
+    else if (kind == 1) dist = 1.0e-30f * ux;
+    else if (kind == 2) dist = 1.0e-18f * (1.0f + uy);
+    else if (kind == 3) scale = 3.0e19f;
+    else if (kind == 4) dist = 0.825f - 0.005f + ((float)((int)(h2 >> 16) & 63) - 32.0f) * 5.9604645e-8f;
+    float4 a0 = make_float4((ux * 40.0f - 20.0f) * scale, (uy * 30.0f - 15.0f) * scale, 0.3f * ux, 0.25f);
+    float4 b0 = make_float4(a0.x + dist * cosf(ang), a0.y + dist * sinf(ang), -0.2f * uy, 0.5f);
+    float mA = 33.0f + ux, iA = 380.0f + uy, mB = 33.0f + uy, iB = 380.0f + ux;
+    if (kind == 5) { mA = 0.0f; iA = 0.0f; mB = 0.0f; iB = 0.0f; }
+    if (kind == 6) { mA = 1.0e25f; mB = 1.0e25f; }
+    const bool skipZero = (h3 & 1u) != 0u;
+    const float baum = (h3 & 2u) != 0u ? KB_BAUMGARTE : KB_TOI_BAUMGARTE, limit = (h3 & 2u) != 0u ? -3.0f * KB_LINEAR_SLOP : -1.5f * KB_LINEAR_SLOP;
+    // reference: the plain operators
+    float4 ra, rb;
+    bool rmoved, rbad = false;
+    const bool rok = kb_position_pair_t<true>(a0, b0, 0.4125f, 0.4125f, mA, iA, mB, iB, baum, limit, skipZero, ra, rb, rmoved, rbad);
+    if (!rmoved) { ra = a0; rb = b0; }
+    // the kernels' sequence
+    sts_f4(wA, a0);
+    sts_f4(wB, b0);
+    float4 a1, b1;
+    bool moved, fbad = false;
+    bool ok = kb_position_pair_t<false>(a0, b0, 0.4125f, 0.4125f, mA, iA, mB, iB, baum, limit, skipZero, a1, b1, moved, fbad);
+    if (moved) {
+      sts_f4(wA, a1);
+      sts_f4(wB, b1);
+    }
+    if (fbad) {
+      ok = kb_position_pair_cold(wA, wB, a0, b0, 0.4125f, 0.4125f, mA, iA, mB, iB, baum, limit, skipZero);
+      ++cold;
+    }
+    const float4 ga = lds_f4(wA), gb = lds_f4(wB);
+    const bool same = sameFloat(ga.x, ra.x) && sameFloat(ga.y, ra.y) && sameFloat(ga.z, ra.z) && sameFloat(ga.w, ra.w) &&
+                      sameFloat(gb.x, rb.x) && sameFloat(gb.y, rb.y) && sameFloat(gb.z, rb.z) && sameFloat(gb.w, rb.w) && ok == rok;
+    if (!same) ++bad;
+  }
+  if (bad) atomicAdd(mismatches + 4, bad);
+  if (cold) atomicAdd(mismatches + 5, cold);
+}
 }  // namespace kb
 extern "C" {
 int kb_selftest_exact_math(int32_t device, int32_t div_rounds_log2, uint64_t* mismatches) {
@@ -1675,12 +1730,14 @@ int kb_selftest_exact_math(int32_t device, int32_t div_rounds_log2, uint64_t* mi
   }
   if (device >= 0) CUDA_TRY(cudaSetDevice(device));
   unsigned long long* d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, 4 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemset(d, 0, 4 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&d, 6 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(d, 0, 6 * sizeof(unsigned long long)));
   kb_selftest_math_kernel<<<148 * 8, 256>>>(1 << div_rounds_log2, d);
   CUDA_TRY(cudaGetLastError());
+  kb_selftest_pair_kernel<<<148 * 4, 256>>>(d);
+  CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaDeviceSynchronize());
-  CUDA_TRY(cudaMemcpy(mismatches, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(mismatches, d, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaFree(d));
   return KB_OK;
 }

@@ -343,8 +343,11 @@ int kb_render(KbHandle* h, const int32_t* env_ids, int32_t num_images, int32_t w
  * csrc/kb_types.cuh): the straight-line square root and reciprocal are compared with sqrtf(x) and 1.0f / x on all 2^32
  * float bit patterns, the division with a / b on 2^(32 + div_rounds_log2) pseudo-random pairs (half of them with both
  * operands inside the fast path's exponent window); inputs the forms hand back to the plain operators are skipped.
- * mismatches: host u64[4] = differing results of (sqrt, reciprocal, division) and the number of comparisons made;
- * bit-exact parity with Box2D's x86-64 arithmetic needs the first three to be 0.  device < 0: the current device. */
+ * mismatches: host u64[6] = differing results of (sqrt, reciprocal, division), the number of comparisons made, and
+ * for the position solver's kilobot-kilobot step run the way the kernels run it (straight-line pass, rows stored, exact
+ * pass out of line when a range test fired) against the plain operators on 2^26 pairs of bodies incl. degenerate ones:
+ * differing rows / verdicts, and how many cases took the exact pass.  Bit-exact parity with Box2D's x86-64 arithmetic
+ * needs entries 0, 1, 2 and 4 to be 0.  device < 0: the current device. */
 int kb_selftest_exact_math(int32_t device, int32_t div_rounds_log2, uint64_t* mismatches);
 
 #ifdef __cplusplus
