@@ -961,64 +961,91 @@ struct Swarm {
     }
     __syncthreads();
     SW_T(3);
-    // ---- thread 0: island DFS (b2World::Solve) in Box2D's order + dependency level of every constraint:
+    // ---- warp 0: island DFS (b2World::Solve) in Box2D's order + dependency level of every constraint:
     // level = 1 + max(level of the earlier constraints that share a dynamic body); the static table never links levels.
-    // A lone thread pays every shared-memory round trip in full, so the search reads ONE word per partner body (its last
-    // level and its flags; a contact is new exactly when the partner has not been popped yet, which is what Box2D's
-    // per-contact island flag says) and fetches the next contact edge and its partner's word while the current one is
-    // worked off (the partners of one body are distinct bodies, so nothing fetched ahead can change underneath).
-    if (tid == 0) {
-      int nOrd = 0, nIslands = 0, maxL = 0;
-      for (int seed = B - 1; seed >= 0; --seed) {   // body list order: newest (highest index) first
-        const uint32_t ws = lds_u32(bw + 4u * (uint32_t)seed);
-        if ((ws & DW_INISLAND) != 0u || (ws & DW_AWAKE) == 0u) continue;
-        int sp = 0;
-        sts_u16(stack, (uint32_t)seed);
-        sp = 1;
-        isl(seed) = (uint32_t)nIslands;
-        sts_u32(bw + 4u * (uint32_t)seed, ws | DW_INISLAND);
-        while (sp > 0) {
-          const int b = (int)lds_u16(stack + 2u * (uint32_t)(--sp));
-          const int s0 = (int)lds_u16(bstart + 2u * (uint32_t)b), s1 = (int)lds_u16(bstart + 2u * (uint32_t)(b + 1));
-          const uint32_t wb = lds_u32(bw + 4u * (uint32_t)b);
-          uint32_t lb = wb & 0xFFFFu;
-          if ((wb & DW_AWAKE) == 0u) wake(b);
-          // two edges in flight: en0 / wo0 = the current edge and its partner's word, en1 = the next edge
-          uint32_t en0 = s0 < s1 ? lds_u32(adj + 4u * (uint32_t)s0) : 0u;
-          uint32_t en1 = s0 + 1 < s1 ? lds_u32(adj + 4u * (uint32_t)(s0 + 1)) : 0u;
-          uint32_t wo0 = (s0 < s1 && (en0 >> 16) != (uint32_t)S) ? lds_u32(bw + 4u * (en0 >> 16)) : 0u;
-          for (int k = s0; k < s1; ++k) {
-            const uint32_t en = en0, wo = wo0;
-            en0 = en1;
-            wo0 = (k + 1 < s1 && (en0 >> 16) != (uint32_t)S) ? lds_u32(bw + 4u * (en0 >> 16)) : 0u;
-            en1 = k + 2 < s1 ? lds_u32(adj + 4u * (uint32_t)(k + 2)) : 0u;
-            const uint32_t t = en & 0xFFFFu, o = en >> 16;
-            const bool dyn = o != (uint32_t)S;
-            if (dyn && (wo & DW_POPPED) != 0u) continue;   // added when the partner was popped
-            const uint32_t lo = dyn ? (wo & 0xFFFFu) : 0u;
-            const uint32_t l = (lb > lo ? lb : lo) + 1u;
-            lb = l;
-            sts_u16(ordT + 2u * (uint32_t)nOrd, t);
-            sts_u16(ordL + 2u * (uint32_t)nOrd, l);
-            sts_u16(ordI + 2u * (uint32_t)nOrd, (uint32_t)nIslands);
-            ++nOrd;
-            maxL = max(maxL, (int)l);
-            if (dyn) {
-              sts_u32(bw + 4u * o, (wo & ~0xFFFFu) | l | DW_INISLAND);
-              if ((wo & DW_INISLAND) == 0u) {
-                isl((int)o) = (uint32_t)nIslands;
-                sts_u16(stack + 2u * (uint32_t)sp, o);
-                ++sp;
+    // The search keeps ONE word per body (its last level and flags; a contact is new exactly when its partner has not
+    // been popped yet, which is what Box2D's per-contact island flag says).  The contact edges of the popped body are
+    // taken by the lanes side by side: the partners of one body are distinct bodies, the new edges get consecutive slots
+    // of the constraint order by ballot rank, and the chain  l_i = max(l_(i-1), lo_i) + 1  over the new edges
+    // (l_(-1) = the body's own last level) is  l_i = i + 1 + max(lb, max_(j<=i)(lo_j - j)):  a prefix maximum over the lanes.
+    // Partners not yet in an island are pushed in edge order (ballot rank), so the stack pops them as Box2D does.
+    if (tid < 32) {
+      const int lane = tid;
+      const uint32_t ltMask = (1u << lane) - 1u;
+      int nOrd = 0, nIslands = 0, maxL = 0;   // (warp-uniform)
+#pragma unroll 1
+      for (int base = ((B - 1) & ~31); base >= 0; base -= 32) {   // body list order: newest (highest index) first
+        for (;;) {
+          const int sb = base + lane;
+          const uint32_t ws = sb < B ? lds_u32(bw + 4u * (uint32_t)sb) : DW_INISLAND;
+          const uint32_t cand = __ballot_sync(0xFFFFFFFFu, (ws & DW_INISLAND) == 0u && (ws & DW_AWAKE) != 0u);
+          if (cand == 0u) break;
+          const int seed = base + 31 - __clz((int)cand);
+          int sp = 1;
+          if (lane == seed - base) {
+            sts_u16(stack, (uint32_t)seed);
+            isl(seed) = (uint32_t)nIslands;
+            sts_u32(bw + 4u * (uint32_t)seed, ws | DW_INISLAND);
+          }
+          __syncwarp();
+          while (sp > 0) {
+            --sp;
+            const int b = (int)lds_u16(stack + 2u * (uint32_t)sp);
+            const int s0 = (int)lds_u16(bstart + 2u * (uint32_t)b), s1 = (int)lds_u16(bstart + 2u * (uint32_t)(b + 1));
+            const uint32_t wb = lds_u32(bw + 4u * (uint32_t)b);
+            int lb = (int)(wb & 0xFFFFu);
+            if ((wb & DW_AWAKE) == 0u && lane == 0) wake(b);
+#pragma unroll 1
+            for (int k0 = s0; k0 < s1; k0 += 32) {
+              const int k = k0 + lane;
+              const bool v = k < s1;
+              const uint32_t en = v ? lds_u32(adj + 4u * (uint32_t)k) : 0u;
+              const uint32_t t = en & 0xFFFFu, o = en >> 16;
+              const bool dyn = v && o != (uint32_t)S;
+              const uint32_t wo = dyn ? lds_u32(bw + 4u * o) : 0u;
+              const bool isNew = v && !(dyn && (wo & DW_POPPED) != 0u);   // else: added when the partner was popped
+              const uint32_t newMask = __ballot_sync(0xFFFFFFFFu, isNew);
+              const uint32_t pushMask = __ballot_sync(0xFFFFFFFFu, isNew && dyn && (wo & DW_INISLAND) == 0u);
+              if (newMask != 0u) {
+                const int r = __popc(newMask & ltMask);
+                int val = isNew ? (int)(wo & 0xFFFFu) - r : -0x40000000;
+                const int width = s1 - k0;
+#pragma unroll 1
+                for (int d = 1; d < 32 && d < width; d <<= 1) {
+                  const int y = __shfl_up_sync(0xFFFFFFFFu, val, d);
+                  if (lane >= d) val = max(val, y);
+                }
+                const int cnt = __popc(newMask);
+                const int l = r + 1 + max(lb, val);
+                if (isNew) {
+                  const uint32_t slot = (uint32_t)(nOrd + r);
+                  sts_u16(ordT + 2u * slot, t);
+                  sts_u16(ordL + 2u * slot, (uint32_t)l);
+                  sts_u16(ordI + 2u * slot, (uint32_t)nIslands);
+                  if (dyn) sts_u32(bw + 4u * o, (wo & ~0xFFFFu) | (uint32_t)l | DW_INISLAND);
+                  if (((pushMask >> lane) & 1u) != 0u) {
+                    isl((int)o) = (uint32_t)nIslands;
+                    sts_u16(stack + 2u * (uint32_t)(sp + __popc(pushMask & ltMask)), o);
+                  }
+                }
+                // the last new edge's level: the highest lane of the chunk holds the maximum over all of them
+                lb = cnt + max(lb, __shfl_sync(0xFFFFFFFFu, val, min(width, 32) - 1));
+                maxL = max(maxL, lb);
+                nOrd += cnt;
+                sp += __popc(pushMask);
               }
             }
+            if (lane == 0) sts_u32(bw + 4u * (uint32_t)b, (uint32_t)lb | DW_INISLAND | DW_POPPED | DW_AWAKE);
+            __syncwarp();
           }
-          sts_u32(bw + 4u * (uint32_t)b, lb | DW_INISLAND | DW_POPPED | DW_AWAKE);
+          ++nIslands;
         }
-        ++nIslands;
       }
-      misc(0) = (uint32_t)nOrd;
-      misc(2) = (uint32_t)nIslands;
-      misc(3) = (uint32_t)maxL;
+      if (lane == 0) {
+        misc(0) = (uint32_t)nOrd;
+        misc(2) = (uint32_t)nIslands;
+        misc(3) = (uint32_t)maxL;
+      }
     }
     __syncthreads();
     const int nOrd = (int)misc(0), nIslDfs = (int)misc(2), maxL = (int)misc(3);
