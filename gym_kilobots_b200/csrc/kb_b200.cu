@@ -779,6 +779,8 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     W.gCellCur = q;
     W.gSorted = q; q += al(2 * L.Pp, 4);
     W.gPcnt = q; q += 4 * L.Pp;
+    q = al(q, 16);
+    W.gFat = q; q += 16 * L.Pp;      // the fat AABBs, staged for the candidate tests (27 per proxy)
     scratch = std::max(scratch, q);
     W.smemBytes = al(W.zScr + scratch, 16);
     if ((size_t)W.smemBytes <= (size_t)prop.sharedMemPerBlockOptin) break;

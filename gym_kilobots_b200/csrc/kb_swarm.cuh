@@ -1250,9 +1250,8 @@ struct Swarm {
 #endif
             relayLeave(wid, k, nTurns, k == nTurns - 1);
 #ifdef KB_PROFILE
-            tp[14] += tr2 - tr1;             // (position relay, warp 0: cycles of its turns' work / cycles handing over)
-            tp[15] += clock64() - tr2;
-            tp[13] += 1000;                  // (turns of warp 0, in thousands, on top of the ~5 kcycles of gather + store)
+            (void)tr1;
+            (void)tr2;
 #endif
           }
         }
@@ -1384,7 +1383,7 @@ struct Swarm {
   // candidate test for the ordered pair (i < j), both dynamic proxies; fi = fat AABB of i
   __device__ __forceinline__ bool newPair(const uint32_t* table, int i, int j, const float4& fi, bool movedI) const {
     if (!movedI && !isMoved(j)) return false;
-    const float4 fj = fatp()[j];
+    const float4 fj = lds_f4(scr(W.gFat) + 16u * (uint32_t)j);   // (staged by findNewContacts)
     const bool overlap = !(fj.x - fi.z > 0.0f || fj.y - fi.w > 0.0f || fi.x - fj.z > 0.0f || fi.y - fj.w > 0.0f);
     if (!overlap) return false;
     return !hashHas(table, (((uint32_t)i << 16) | (uint32_t)j) + 1u);
@@ -1467,10 +1466,17 @@ struct Swarm {
       const uint32_t cs = lds_u32(pcnt + 4u * (uint32_t)p);
       sts_u16(sorted + 2u * (lds_u32(cellStart + 4u * (cs >> 12)) + (cs & 0xFFFu)), (uint32_t)p);
     }
+    // every proxy's fat AABB into shared memory: each is read by ~27 candidate tests (two passes), from L2 otherwise
+    for (int p = tid; p < P; p += NT) sts_f4(scr(W.gFat) + 16u * (uint32_t)p, fatp()[p]);
     __syncthreads();
     const int rad = (int)misc(4);
     uint32_t tests = 0u;
     bool overflow = false;
+#ifdef KB_PROFILE
+    __syncthreads();
+    const long long tf0 = clock64();
+    tp[14] += tf0 - tlast;   // (find new contacts: pair hash + grid build)
+#endif
     // ---- table edges first (lowest proxy ids): every dynamic proxy j against edge i, block-wide
     for (int i = 0; i < nWall; ++i) {
       const float4 fi = fatp()[i];
@@ -1498,6 +1504,10 @@ struct Swarm {
         nC = min(nC + total, L.Cmax);
       }
     }
+#ifdef KB_PROFILE
+    __syncthreads();
+    (void)tf0;
+#endif
     // ---- dynamic against dynamic through the grid: proxy i owns its pairs (i, j > i)
 #pragma unroll 1
     for (int base = nWall; base < P; base += NT) {
@@ -1523,8 +1533,14 @@ struct Swarm {
             }
           }
       }
+#ifdef KB_PROFILE
+      const long long tg0 = clock64();
+#endif
       int total;
       int dst = nC + blockExScan(cnt, &total);
+#ifdef KB_PROFILE
+      tp[15] += clock64() - tg0;   // (find new contacts: thread 0 waiting for the slowest thread's candidate tests)
+#endif
       if (cnt > 0) {
         wake(pbody(i));
         // emit the partners in ascending order: repeated selection of the smallest j above the last one

@@ -15,7 +15,7 @@ CSRC = os.path.join(ROOT, "gym_kilobots_b200", "csrc")
 PROF = os.path.join(ROOT, "build", "lib_prof.so")
 NAMES = ["sense/light", "collide", "touching list", "body lists (CSR)", "island DFS (thread 0)", "rows+integrate+init",
          "warm start + velocity", "store + integrate", "position", "transform + sleep", "sync fixtures", "find new contacts",
-         "toi", "gather + store", "(position relay, warp 0: work of its turns)", "(position relay, warp 0: handing over)"]
+         "toi", "gather + store", "(of find new contacts: pair hash + grid build)", "(of find new contacts: thread 0 waiting at the scans of the grid pass)"]
 
 if sys.argv[1] == "build":
     os.makedirs(os.path.dirname(PROF), exist_ok=True)
@@ -51,8 +51,8 @@ for t in range(T):
         cnow = nb.counters().astype(np.float64)
         c = cnow - cprev
         cprev = cnow
-        print("env-step %d: %.2f Mcycles per env-step (mean; max %.2f); touching/substep %.0f, levels/substep %.0f, position sweeps x islands/substep %.1f, islands/substep %.1f" % (
-            t, tot.mean() / 1e6, tot.max() / 1e6, c[:, 2].sum() / c[:, 0].sum(), c[:, 3].sum() / c[:, 0].sum(), c[:, 4].sum() / c[:, 0].sum(), c[:, 7].sum() / c[:, 0].sum()))
+        print("env-step %d: %.2f Mcycles per env-step (mean; max %.2f); touching/substep %.0f, levels/substep %.0f, position sweeps x islands/substep %.1f, islands/substep %.1f, pair tests/substep %.0f" % (
+            t, tot.mean() / 1e6, tot.max() / 1e6, c[:, 2].sum() / c[:, 0].sum(), c[:, 3].sum() / c[:, 0].sum(), c[:, 4].sum() / c[:, 0].sum(), c[:, 7].sum() / c[:, 0].sum(), c[:, 6].sum() / c[:, 0].sum()))
         for i, n in enumerate(NAMES):
             if p[:, i].mean() > 0:
                 print("   %-28s %9.0f kcycles  %5.1f %%" % (n, p[:, i].mean() / 1e3, 100 * p[:, i].mean() / tot.mean()))
