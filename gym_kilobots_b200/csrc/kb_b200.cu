@@ -781,6 +781,7 @@ int kb_create(const KbSceneDesc* scenes, int32_t num_scenes, const int32_t* env_
     W.gPcnt = q; q += 4 * L.Pp;
     q = al(q, 16);
     W.gFat = q; q += 16 * L.Pp;      // the fat AABBs, staged for the candidate tests (27 per proxy)
+    W.gCand = q; q += 2 * 12 * std::min(512, al(L.Pp, 32));   // per live thread: the partners whose fat AABBs overlap (KB_SW_CAND u16 each)
     scratch = std::max(scratch, q);
     W.smemBytes = al(W.zScr + scratch, 16);
     if ((size_t)W.smemBytes <= (size_t)prop.sharedMemPerBlockOptin) break;

@@ -1508,34 +1508,106 @@ struct Swarm {
     __syncthreads();
     (void)tf0;
 #endif
-    // ---- dynamic against dynamic through the grid: proxy i owns its pairs (i, j > i)
+    // ---- dynamic against dynamic through the grid: proxy i owns its pairs (i, j > i).
+    // The walk over the (2 rad + 1)^2 cells is WARP-COHERENT: every lane takes the same number of cells (clipped ones are
+    // empty ranges) and the warp's widest cell sets the inner trip count, so the lanes stay on one path through the loads
+    // and comparisons and only the hash look-up of an overlapping pair diverges (with each lane walking its own ragged
+    // ranges the warp serialised up to 32 different paths: 0.45 of 0.5 Mcycles per sub-step at 1024 kilobots).
+    // The walk only COLLECTS the partners whose fat AABBs overlap (at most KB_SW_CAND per proxy in a per-thread row of
+    // shared memory); whether such a pair already has a contact is then asked of the L2-resident hash for all of them at
+    // once (independent loads in flight together: one L2 round trip per proxy instead of one per candidate, on a path the
+    // whole warp waits on), and the new ones are emitted in ascending order from the same row -- no second walk.
+    constexpr int KB_SW_CAND = 12;
+    const uint32_t candRow = scr(W.gCand) + 2u * (uint32_t)(KB_SW_CAND * tid);
+    const int side = 2 * rad + 1;
 #pragma unroll 1
     for (int base = nWall; base < P; base += NT) {
       const int i = base + tid;
-      int cnt = 0;
+      const bool live = i < P;
       float4 fi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       int cx = 0, cy = 0;
       bool movedI = false;
-      if (i < P) {
-        fi = fatp()[i];
+      if (live) {
+        fi = lds_f4(scr(W.gFat) + 16u * (uint32_t)i);
         movedI = isMoved(i);
         cx = cellOf(0.5f * (fi.x + fi.z), W.gx0, W.gx);
         cy = cellOf(0.5f * (fi.y + fi.w), W.gy0, W.gy);
+      }
+      int nCand = 0, cnt = 0;
+#pragma unroll 1
+      for (int ci = 0; ci < side * side; ++ci) {
+        const int xx = cx - rad + ci % side, yy = cy - rad + ci / side;
+        int s0 = 0, s1 = 0;
+        if (live && xx >= 0 && xx < W.gx && yy >= 0 && yy < W.gy) {
+          const int c = xx + W.gx * yy;
+          s0 = (int)lds_u32(cellStart + 4u * (uint32_t)c);
+          s1 = (int)lds_u32(cellStart + 4u * (uint32_t)(c + 1));
+        }
+        const int nmax = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)(s1 - s0));
+#pragma unroll 1
+        for (int t = 0; t < nmax; ++t) {
+          const bool v = s0 + t < s1;
+          const int j = v ? (int)lds_u16(sorted + 2u * (uint32_t)(s0 + t)) : 0;
+          bool cand = v && j > i && (movedI || isMoved(j));
+          if (cand) {
+            tests += 1u;
+            const float4 fj = lds_f4(scr(W.gFat) + 16u * (uint32_t)j);
+            cand = !(fj.x - fi.z > 0.0f || fj.y - fi.w > 0.0f || fi.x - fj.z > 0.0f || fi.y - fj.w > 0.0f);
+          }
+          if (cand) {
+            if (nCand < KB_SW_CAND) sts_u16(candRow + 2u * (uint32_t)nCand, (uint32_t)j);
+            ++nCand;   // (more than the row holds: the plain walk below)
+          }
+        }
+      }
+      // first probe of every collected pair, all in flight together; a collision continues the probe sequence
+      uint32_t isNew = 0u;
+      {
+        uint32_t probe[KB_SW_CAND], slot[KB_SW_CAND], key[KB_SW_CAND];
+#pragma unroll
+        for (int q = 0; q < KB_SW_CAND; ++q) {
+          const uint32_t j = q < nCand ? lds_u16(candRow + 2u * (uint32_t)q) : 0u;
+          key[q] = (((uint32_t)i << 16) | j) + 1u;
+          slot[q] = (key[q] * 2654435761u) >> W.hashShift;
+          probe[q] = q < nCand ? __ldcg(table + slot[q]) : key[q];
+        }
+#pragma unroll
+        for (int q = 0; q < KB_SW_CAND; ++q) {
+          if (q < nCand && probe[q] != key[q]) {
+            bool found = false;
+            uint32_t k = probe[q], h = slot[q];
+            while (k != 0u) {
+              h = (h + 1u) & (uint32_t)(W.hashSize - 1);
+              k = __ldcg(table + h);
+              if (k == key[q]) {
+                found = true;
+                break;
+              }
+            }
+            if (!found) isNew |= 1u << q;
+          }
+        }
+      }
+      const bool rowFull = nCand > KB_SW_CAND;   // more overlapping partners than the row holds
+      nCand = min(nCand, KB_SW_CAND);
+      cnt = __popc(isNew);
+#ifdef KB_PROFILE
+      const long long tg0 = clock64();
+#endif
+      if (rowFull) {
+        // (never at the densities a table holds: a fat AABB overlaps a dozen others only in a heap of stacked spawns)
+        // count and emit by the plain walk: repeated selection of the smallest new partner above the last one
+        cnt = 0;
         for (int yy = max(cy - rad, 0); yy <= min(cy + rad, W.gy - 1); ++yy)
           for (int xx = max(cx - rad, 0); xx <= min(cx + rad, W.gx - 1); ++xx) {
             const int c = xx + W.gx * yy;
             const int s0 = (int)lds_u32(cellStart + 4u * (uint32_t)c), s1 = (int)lds_u32(cellStart + 4u * (uint32_t)(c + 1));
             for (int k = s0; k < s1; ++k) {
               const int j = (int)lds_u16(sorted + 2u * (uint32_t)k);
-              if (j <= i) continue;
-              if (movedI || isMoved(j)) tests += 1u;
-              if (newPair(table, i, j, fi, movedI)) ++cnt;
+              if (j > i && newPair(table, i, j, fi, movedI)) ++cnt;
             }
           }
       }
-#ifdef KB_PROFILE
-      const long long tg0 = clock64();
-#endif
       int total;
       int dst = nC + blockExScan(cnt, &total);
 #ifdef KB_PROFILE
@@ -1543,19 +1615,26 @@ struct Swarm {
 #endif
       if (cnt > 0) {
         wake(pbody(i));
-        // emit the partners in ascending order: repeated selection of the smallest j above the last one
+        // emit the partners in ascending order: repeated selection of the smallest new j above the last one
         int last = i;
         for (int n = 0; n < cnt; ++n) {
           int best = 0x7FFFFFFF;
-          for (int yy = max(cy - rad, 0); yy <= min(cy + rad, W.gy - 1); ++yy)
-            for (int xx = max(cx - rad, 0); xx <= min(cx + rad, W.gx - 1); ++xx) {
-              const int c = xx + W.gx * yy;
-              const int s0 = (int)lds_u32(cellStart + 4u * (uint32_t)c), s1 = (int)lds_u32(cellStart + 4u * (uint32_t)(c + 1));
-              for (int k = s0; k < s1; ++k) {
-                const int j = (int)lds_u16(sorted + 2u * (uint32_t)k);
-                if (j > last && j < best && newPair(table, i, j, fi, movedI)) best = j;
-              }
+          if (!rowFull) {
+            for (int q = 0; q < nCand; ++q) {
+              const int j = (int)lds_u16(candRow + 2u * (uint32_t)q);
+              if (((isNew >> q) & 1u) != 0u && j > last && j < best) best = j;
             }
+          } else {
+            for (int yy = max(cy - rad, 0); yy <= min(cy + rad, W.gy - 1); ++yy)
+              for (int xx = max(cx - rad, 0); xx <= min(cx + rad, W.gx - 1); ++xx) {
+                const int c = xx + W.gx * yy;
+                const int s0 = (int)lds_u32(cellStart + 4u * (uint32_t)c), s1 = (int)lds_u32(cellStart + 4u * (uint32_t)(c + 1));
+                for (int k = s0; k < s1; ++k) {
+                  const int j = (int)lds_u16(sorted + 2u * (uint32_t)k);
+                  if (j > last && j < best && newPair(table, i, j, fi, movedI)) best = j;
+                }
+              }
+          }
           if (dst < L.Cmax) {
             cwp()[dst] = CI_ENABLED;
             cpairp()[dst] = (uint32_t)i | ((uint32_t)best << 16);
