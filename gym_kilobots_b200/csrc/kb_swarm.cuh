@@ -1232,6 +1232,10 @@ struct Swarm {
               sB = pos4((int)(bb >> 16));
               if ((int)(bb & 0xFFFFu) != S) wA = sA;
             }
+            // (everything a row-step needs besides the two body rows is in registers before the warp's turn: also the
+            //  address of the island's state byte and the constant stored there)
+            const uint32_t islA = islStateAddr((int)(ei & 0x7FFFu)), three = 3u;
+            const bool fastE = (ei & 0x8000u) != 0u;
             relayEnter(wid, k, nTurns, k == 0);
 #ifdef KB_PROFILE
             const long long tr1 = clock64();
@@ -1240,8 +1244,8 @@ struct Swarm {
             for (int gg = 0; gg < RG; ++gg) {
               // (here one guard is cheaper than running the idle lanes on the dummy row: the sqrt / division paths diverge)
               if (g == gg && mine) {
-                const bool ok = solvePositionCore(sA, sB, wA, sB, (ei & 0x8000u) != 0u, r0, r1, r2, KB_BAUMGARTE, -3.0f * KB_LINEAR_SLOP, true);
-                if (!ok) sts_u8(islStateAddr((int)(ei & 0x7FFFu)), 3u);
+                const bool ok = solvePositionCore(sA, sB, wA, sB, fastE, r0, r1, r2, KB_BAUMGARTE, -3.0f * KB_LINEAR_SLOP, true);
+                if (!ok) sts_u8(islA, three);
               }
               __syncwarp();
             }
