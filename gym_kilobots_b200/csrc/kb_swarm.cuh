@@ -834,18 +834,16 @@ struct Swarm {
     __syncwarp();   // the warp's shared-memory stores are all issued before it arrives
     asm volatile("bar.arrive %0, 64;" ::"r"(1 + w) : "memory");
   }
-  // turn order inside one pass over the turns 0..nTurns-1, repeated without a block-wide barrier in between
-  __device__ __forceinline__ void relayEnter(int wid, int k, int nTurns, bool firstTurn) const {
-    if (firstTurn) return;
-    const int prev = (k == 0 ? nTurns - 1 : k - 1) % NR;
-    if (prev != wid) relayWait(wid);
-    else __syncwarp();
+  // turn order inside one pass over the turns 0..nTurns-1, repeated without a block-wide barrier in between.  The successor
+  // is worked out BEFORE the warp's turn (relayNext), so that the hand-over is one instruction after the last row.  A warp
+  // that is its own successor (fewer turns than relay warps, or the wrap-around) arrives on its own barrier and finds the
+  // 64 threads complete when it waits.
+  __device__ __forceinline__ void relayEnter(int wid, bool firstTurn) const {
+    if (!firstTurn) relayWait(wid);
   }
-  __device__ __forceinline__ void relayLeave(int wid, int k, int nTurns, bool lastTurn) const {
-    if (lastTurn) return;
-    const int next = (k == nTurns - 1 ? 0 : k + 1) % NR;
-    if (next != wid) relayPass(next);
-    else __syncwarp();
+  __device__ __forceinline__ int relayNext(int k, int nTurns) const { return (k == nTurns - 1 ? 0 : k + 1) % NR; }
+  __device__ __forceinline__ void relayLeave(int next, bool lastTurn) const {
+    if (!lastTurn) relayPass(next);
   }
 
   // b2World::Solve
@@ -1144,14 +1142,25 @@ struct Swarm {
               sB = vel4((int)(bb >> 16));
               if ((int)(bb & 0xFFFFu) != S) wA = sA;
             }
-            relayEnter(wid, k, nTurns, pass == 0 && k == 0);
+            // the rows every step loads from and stores to (the lane's own in its group's step, the dummy row otherwise):
+            // selected here, off the dependent chain
+            uint32_t aS[RG], bS[RG], cS[RG];
+#pragma unroll
+            for (int gg = 0; gg < RG; ++gg) {
+              const bool act = g == gg;
+              aS[gg] = act ? sA.a : dm.a;
+              bS[gg] = act ? sB.a : dm.a;
+              cS[gg] = act ? wA.a : dm.a;
+            }
+            const int nextW = relayNext(k, nTurns);
+            relayEnter(wid, pass == 0 && k == 0);
             // the levels of the turn, one after the other: every lane runs every step (no branches on the way), the lanes
             // outside the step's group on the dummy row
             float imp = 0.0f;
 #pragma unroll
             for (int gg = 0; gg < RG; ++gg) {
               const bool act = g == gg;
-              const SF4 a = act ? sA : dm, b = act ? sB : dm, c = act ? wA : dm;
+              const SF4 a{aS[gg]}, b{bS[gg]}, c{cS[gg]};
               if (pass == 0) {
                 warmStartCore(a, b, c, b, r0, r1, r2);
               } else {
@@ -1160,7 +1169,7 @@ struct Swarm {
               }
               __syncwarp();
             }
-            relayLeave(wid, k, nTurns, pass == passes - 1 && k == nTurns - 1);
+            relayLeave(nextW, pass == passes - 1 && k == nTurns - 1);
             if (mine && pass != 0) rec4(3 * e).set(3, imp);
           }
         }
@@ -1236,7 +1245,8 @@ struct Swarm {
             //  address of the island's state byte and the constant stored there)
             const uint32_t islA = islStateAddr((int)(ei & 0x7FFFu)), three = 3u;
             const bool fastE = (ei & 0x8000u) != 0u;
-            relayEnter(wid, k, nTurns, k == 0);
+            const int nextW = relayNext(k, nTurns);
+            relayEnter(wid, k == 0);
 #ifdef KB_PROFILE
             const long long tr1 = clock64();
 #endif
@@ -1252,7 +1262,7 @@ struct Swarm {
 #ifdef KB_PROFILE
             const long long tr2 = clock64();
 #endif
-            relayLeave(wid, k, nTurns, k == nTurns - 1);
+            relayLeave(nextW, k == nTurns - 1);
 #ifdef KB_PROFILE
             (void)tr1;
             (void)tr2;
