@@ -1157,17 +1157,19 @@ struct Swarm {
             // the levels of the turn, one after the other: every lane runs every step (no branches on the way), the lanes
             // outside the step's group on the dummy row
             float imp = 0.0f;
+            if (pass == 0) {   // (one uniform branch per turn, not per step)
 #pragma unroll
-            for (int gg = 0; gg < RG; ++gg) {
-              const bool act = g == gg;
-              const SF4 a{aS[gg]}, b{bS[gg]}, c{cS[gg]};
-              if (pass == 0) {
-                warmStartCore(a, b, c, b, r0, r1, r2);
-              } else {
-                const float ni = solveVelocityCore(a, b, c, b, r0, r1, r2);
-                imp = act ? ni : imp;
+              for (int gg = 0; gg < RG; ++gg) {
+                warmStartCore(SF4{aS[gg]}, SF4{bS[gg]}, SF4{cS[gg]}, SF4{bS[gg]}, r0, r1, r2);
+                __syncwarp();
               }
-              __syncwarp();
+            } else {
+#pragma unroll
+              for (int gg = 0; gg < RG; ++gg) {
+                const float ni = solveVelocityCore(SF4{aS[gg]}, SF4{bS[gg]}, SF4{cS[gg]}, SF4{bS[gg]}, r0, r1, r2);
+                imp = g == gg ? ni : imp;
+                __syncwarp();
+              }
             }
             relayLeave(nextW, pass == passes - 1 && k == nTurns - 1);
             if (mine && pass != 0) rec4(3 * e).set(3, imp);
