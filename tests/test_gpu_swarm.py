@@ -94,6 +94,23 @@ def test_swarm_tier_more_than_62_bodies(oracle, native):
     assert _tier(nb) in SWARM_BLOCKS
 
 
+def test_swarm_tier_stacked_heap(oracle, native):
+    """90 kilobots spawned on top of each other (a clipped Gaussian of 1 cm, the reference's spawn taken to the extreme)
+    with a slot for every pair: bodies with dozens of contact edges (the island search takes them 32 at a time), fat AABBs
+    overlapping more partners than the broadphase's candidate row holds (the plain walk), levels far wider than a row of
+    the relay, coincident centres (the position solver's exact pass)."""
+    n = 90
+    sc = SC.swarm_corner(2, n=n, spread=.07, corner=False)
+    rng = np.random.default_rng(5)
+    sc.body_pose[:, :, :2] = np.clip(rng.normal(0.0, 0.01, (2, n, 2)), -0.03, 0.03)
+    sc.body_pose[0, 1, :2] = sc.body_pose[0, 0, :2]          # two exactly coincident kilobots
+    sc.max_contacts = n * (n - 1) // 2 + 4 * n
+    ob, nb = run_parity(oracle, native, sc, steps=4)
+    assert _tier(nb) in SWARM_BLOCKS
+    pr, ct = nb.contacts()
+    assert ct.max() > 1500 and not nb.get_status().any()
+
+
 def test_swarm_direct_control_and_kinds(oracle, native, monkeypatch):
     """Velocity- and acceleration-controlled kilobots (KB_ACTION_KILOBOTS) on the swarm tier."""
     monkeypatch.setenv("KB_FORCE_SWARM", "1")
