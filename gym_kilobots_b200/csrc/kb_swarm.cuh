@@ -1,13 +1,14 @@
-// kb_swarm.cuh -- the large-swarm tier: ONE CTA per environment, as many kilobots as fit one SM's shared memory
-// (about 1700; proxy ids are 11 bits wide).
+// kb_swarm.cuh -- the large-swarm tier: ONE CTA per environment, up to 2040 kilobots (proxy ids are 11 bits wide; the
+// shared-memory image is ~35 bytes per body + ~21 per touching contact of capacity).
 //
 // BASELINE.json configs[3] ("256 envs x 1024 kilobots, grid broadphase, dense contacts"): the reference puts no
 // bound on kilobots per env (gym_kilobots/envs/kilobots_env.py:105-109, yaml_kilobots_env.py:327-354 kilobots.num),
 // and the lane-group kernel of kb_step.cuh stops at 62 bodies (64-bit adjacency masks).  Same semantics, same
 // Box2D orderings, different data structures:
-//   * body state (c, a, sleepTime | v, w, flags | q) stays in shared memory for all sub-steps of an action; fat
-//     AABBs, the persistent contact list (flags word + proxy-pair word + 8-word manifold record per contact),
-//     controller state and sweeps live in the env's blob in HBM/L2 and are streamed by the data-parallel phases;
+//   * body state (c, a, sleepTime | v, w, flags) stays in shared memory for all sub-steps of an action; fat AABBs,
+//     the persistent contact list (flags word + proxy-pair word + 8-word manifold record per contact), controller
+//     state, sweeps, (sin, cos), the level schedule, the solver's records and the pair hash live in the env's
+//     L2-resident blob and are streamed by the data-parallel phases / prefetched by the relay's waiting warps;
 //   * broadphase = per-env UNIFORM GRID over the fat-AABB centres of the dynamic proxies (counting sort; the
 //     per-cell counts are accumulated with warp-aggregated atomics: __match_any_sync groups the lanes that hit the
 //     same cell, the leader adds the group's popcount and the ranks come from the lane mask).  Every proxy owns
@@ -16,10 +17,13 @@
 //     a block-wide exclusive scan over the per-proxy counts places the new pairs in (proxyA, proxyB)-sorted order
 //     -- exactly the order b2BroadPhase::UpdatePairs hands them to AddPair, so contact creation order matches;
 //   * islands: per-body CSR lists over the touching list (descending contact index == Box2D's LIFO contact-edge
-//     lists), serial DFS in Box2D's order on one thread, dependency level per constraint, counting sort by level;
+//     lists), DFS in Box2D's order on warp 0 (a body's contact edges side by side on the lanes), dependency level
+//     per constraint, counting sort by level, wide levels cut into rows of at most 8;
 //   * solver: the constraints of one level touch disjoint bodies, so a sweep over levels is bit-identical to
-//     Box2D's sequential sweep.  Levels are executed by warp 0 (a lattice swarm is ONE island whose level structure
-//     is a long chain: 1-3 constraints per level), records (2 x float4 per constraint) in shared memory.
+//     Box2D's sequential sweep.  A lattice swarm is ONE island whose level structure is a long chain (1-3
+//     constraints per level): the rows are executed as a RELAY over the CTA's warps -- four rows per turn in lane
+//     groups of eight, the turn's entries and records (3 x float4 per constraint) fetched from L2 while the seven
+//     turns before it run, hand-over on named barriers (see "relay" below and DESIGN.md section 6).
 // Scope of this tier (checked by kb_create): every dynamic body is a kilobot (one circle fixture at the body origin,
 // friction 0, restitution 0), no pushable objects (M = 0); the table's chain edges are the only other proxies.
 // All constraints are therefore "simple" (one manifold point, frictionless, no restitution): kb_step.cuh's
@@ -31,8 +35,8 @@
 namespace kb {
 
 // threads per CTA: 512, 256 or 128 -- the widest block that still lets as many CTAs share an SM as its shared memory holds
-// (124 registers per thread: 512 threads x 1 CTA, 256 x 2, 128 x 4).  A second CTA on the SM overlaps perfectly with the
-// first (the solver keeps ONE warp busy): 296 envs of 484 kilobots take as long as 148.
+// (<= 128 registers per thread: 512 threads x 1 CTA, 256 x 2, 128 x 4).  A second CTA on the SM overlaps with the first
+// (the solver's dependent chain keeps one warp at a time busy): 296 envs of 484 kilobots take as long as 148.
 #define KB_SWARM_THREADS_MAX 512
 #define KB_SWARM_MAX_BODIES 2040   /* 11-bit proxy ids (bodies + table edges < 2048) */
 
@@ -122,7 +126,7 @@ struct Swarm {
   __device__ __forceinline__ SU32 misc(int i) const { return SU32{sa + W.zMisc + 4u * (uint32_t)i}; }
   __device__ __forceinline__ SU16 isl(int b) const { return SU16{sa + W.zIsl + 2u * (uint32_t)b}; }
   __device__ __forceinline__ uint32_t islStateAddr(int i) const { return sa + W.zIslState + (uint32_t)i; }
-  // the level schedule and the solver's records live in the blob (L2-resident, streamed by warp 0 level by level): that
+  // the level schedule and the solver's records live in the blob (L2-resident, fetched by the relay's waiting warps): that
   // keeps the CTA's shared memory small enough for TWO CTAs per SM at 1024 kilobots, and a second CTA overlaps perfectly
   __device__ __forceinline__ GU32 ent0(int e) const { return GU32{reinterpret_cast<uint32_t*>(blob + W.oEnt0) + e}; }        // bA | bB << 16
   __device__ __forceinline__ GU16 entC(int e) const { return GU16{reinterpret_cast<uint16_t*>(blob + W.oEntC) + e}; }        // contact index
